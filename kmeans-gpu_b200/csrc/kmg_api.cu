@@ -1,0 +1,1027 @@
+// kmg_api.cu — host side of libkmeans_gpu.so: context, per-call workspaces, k-means job
+// orchestration and the extern "C" entry points declared in include/kmeans_gpu.h.
+//
+// There is no CPU compute path in this file: every operation that the reference runs on the GPU
+// (core/shaders/*.wgsl) is a kernel launch here.  The only host arithmetic is what the reference
+// also does on the host (the `palette` crate conversions, kmg_host.cpp).
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <dlfcn.h>
+
+#include "../../include/kmeans_gpu.h"
+#include "kmg_kernels.cuh"
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define KMG_HAVE_NCCL_HEADER 1
+#else
+#define KMG_HAVE_NCCL_HEADER 0
+#endif
+
+using namespace kmg;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+
+static thread_local std::string g_last_error = "";
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(e__ == cudaErrorMemoryAllocation ? KMG_ERR_OOM : KMG_ERR_CUDA, "%s failed: %s", \
+                  #expr, cudaGetErrorString(e__));                                                \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int r__ = (expr);        \
+    if (r__ != KMG_OK) return r__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen, so single-GPU users need no NCCL at link or load time.
+
+#if KMG_HAVE_NCCL_HEADER
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // If the process already loaded an NCCL (e.g. torch's bundled one) the SONAME lookup reuses it.
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+  });
+  return api;
+}
+#define NC(expr)                                                                                     \
+  do {                                                                                               \
+    ncclResult_t r__ = (expr);                                                                       \
+    if (r__ != ncclSuccess) return fail(KMG_ERR_NCCL, "%s failed: %s", #expr, nccl_api().GetErrorString(r__)); \
+  } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// context / workspace
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return KMG_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(KMG_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return KMG_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Workspace {
+  cudaStream_t stream = nullptr;
+  Buf in, out, small, work, dmin, blob;
+  JobState* h_state = nullptr;  // pinned
+  void release() {
+    in.release();
+    out.release();
+    small.release();
+    work.release();
+    dmin.release();
+    blob.release();
+    if (h_state) cudaFreeHost(h_state);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+struct kmg_ctx {
+  int device = 0;
+  int sms = 0;
+  float* d_lut = nullptr;
+  cudaStream_t stream = nullptr;  // context stream for device-resident calls with stream == NULL
+  std::mutex mu;
+  std::vector<Workspace*> pool;
+  std::atomic<uint64_t> launches{0};
+  int occ_private8 = 1, occ_private16 = 1, occ_private32 = 1;
+  // multi-GPU
+  int n_ranks = 1, rank = 0;
+#if KMG_HAVE_NCCL_HEADER
+  ncclComm_t comm = nullptr;
+#endif
+};
+
+struct kmg_job {
+  kmg_ctx* ctx = nullptr;
+  JobPtrs P{};
+  void* blob = nullptr;
+  bool owns_blob = false;
+  float* dmin = nullptr;
+  bool owns_dmin = false;
+  JobState* h_state = nullptr;  // pinned
+  bool owns_h_state = false;
+  const float4* work = nullptr;
+  uint32_t w = 0, h = 0, k = 0;
+  int color_space = 0;
+  kmg_opts opts{};
+  // shard of a distributed image
+  bool sharded = false;
+  uint32_t global_w = 0, global_h = 0, row_offset = 0;
+  float* d_xfer = nullptr;  // 4 floats, colour broadcast during distributed init
+};
+
+static size_t job_blob_bytes(uint32_t k) {
+  size_t kp = pad32(k);
+  return 256 + (size_t)k * 16 + kp * sizeof(CentRec) + (size_t)ACC_COPIES * k * 4 * 8 + (size_t)k * 8 + (size_t)k * 4 + 64;
+}
+static void job_carve(kmg_job* j, void* blob) {
+  unsigned char* b = (unsigned char*)blob;
+  size_t kp = pad32(j->k);
+  j->P.st = (JobState*)b;
+  b += 256;
+  j->P.cent = (float4*)b;
+  b += (size_t)j->k * 16;
+  j->P.tab = (CentRec*)b;
+  b += kp * sizeof(CentRec);
+  j->P.acc = (long long*)b;
+  b += (size_t)ACC_COPIES * j->k * 4 * 8;
+  j->P.keys = (unsigned long long*)b;
+  b += (size_t)j->k * 8;
+  j->P.pal = (uint32_t*)b;
+  b += (size_t)j->k * 4;
+  j->d_xfer = (float*)(((uintptr_t)b + 15) & ~(uintptr_t)15);
+}
+
+static Workspace* ws_acquire(kmg_ctx* ctx) {
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->pool.empty()) {
+      Workspace* w = ctx->pool.back();
+      ctx->pool.pop_back();
+      return w;
+    }
+  }
+  Workspace* w = new Workspace();
+  if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&w->h_state, sizeof(JobState)) != cudaSuccess) {
+    cudaGetLastError();
+    w->release();
+    delete w;
+    return nullptr;
+  }
+  return w;
+}
+static void ws_release(kmg_ctx* ctx, Workspace* w) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->pool.push_back(w);
+}
+struct WsGuard {
+  kmg_ctx* ctx;
+  Workspace* ws;
+  ~WsGuard() {
+    if (ws) ws_release(ctx, ws);
+  }
+};
+
+static inline int grid_for(kmg_ctx* ctx, unsigned long long items, int per_block, int blocks_per_sm) {
+  unsigned long long blocks = (items + per_block - 1) / per_block;
+  unsigned long long cap = (unsigned long long)ctx->sms * blocks_per_sm;
+  if (blocks < 1) blocks = 1;
+  return (int)std::min(blocks, cap);
+}
+
+#define LAUNCHED(ctx) (ctx)->launches.fetch_add(1, std::memory_order_relaxed)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+
+extern "C" int kmg_abi_version(void) { return KMG_ABI_VERSION; }
+extern "C" const char* kmg_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" void kmg_default_opts(kmg_opts* o) {
+  if (!o) return;
+  o->struct_size = sizeof(kmg_opts);
+  o->max_dim = 256;
+  o->max_iter = 128;
+  o->check_every = 8;
+  o->convergence = -1.0f;
+  o->seed_x_frac = 0.5625f;
+  o->seed_y_frac = 0.93359375f;
+  o->seed_x = -1;
+  o->seed_y = -1;
+}
+
+static kmg_opts resolve_opts(const kmg_opts* in) {
+  kmg_opts o;
+  kmg_default_opts(&o);
+  if (in) {
+    size_t n = std::min<size_t>(in->struct_size ? in->struct_size : sizeof(kmg_opts), sizeof(kmg_opts));
+    memcpy(&o, in, n);
+    o.struct_size = sizeof(kmg_opts);
+  }
+  return o;
+}
+
+extern "C" int kmg_create(int device, kmg_ctx** out) {
+  if (!out) return fail(KMG_ERR_BAD_ARG, "kmg_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(KMG_ERR_CUDA, "kmg_create: no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= count) return fail(KMG_ERR_BAD_ARG, "kmg_create: device %d out of range [0,%d)", device, count);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(KMG_ERR_UNSUPPORTED, "kmg_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+  kmg_ctx* ctx = new kmg_ctx();
+  ctx->device = device;
+  ctx->sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc((void**)&ctx->d_lut, 256 * sizeof(float)));
+  k_build_srgb_table<<<1, 256, 0, ctx->stream>>>(ctx->d_lut);
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  // opt in to > 48 KiB dynamic shared memory
+  CU(cudaFuncSetAttribute(k_lloyd_private<8, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+  CU(cudaFuncSetAttribute(k_lloyd_private<16, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16));
+  CU(cudaFuncSetAttribute(k_lloyd_private<32, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 128 * 16));
+  const int big = MAX_K * (int)(sizeof(CentRec) + 4);
+  CU(cudaFuncSetAttribute(k_lloyd_global<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU(cudaFuncSetAttribute(k_assign<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU(cudaFuncSetAttribute(k_remap<0, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU(cudaFuncSetAttribute(k_remap<1, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, k_lloyd_private<8, 256, 4>, 256, 8 * 256 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, k_lloyd_private<16, 256, 4>, 256, 16 * 256 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, k_lloyd_private<32, 128, 4>, 128, 32 * 128 * 16));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = ctx;
+  return KMG_OK;
+}
+
+extern "C" void kmg_destroy(kmg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+#if KMG_HAVE_NCCL_HEADER
+  if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+#endif
+  for (Workspace* w : ctx->pool) {
+    w->release();
+    delete w;
+  }
+  if (ctx->d_lut) cudaFree(ctx->d_lut);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" uint64_t kmg_launch_count(kmg_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+extern "C" void kmg_resized_dims(uint32_t w, uint32_t h, uint32_t max_size, uint32_t* ow, uint32_t* oh) {
+  // core/src/structures.rs:79-89 (strict `width > height`; f32 arithmetic, truncation, max(1))
+  uint32_t nw, nh;
+  if (w > h) {
+    nw = max_size;
+    nh = std::max<uint32_t>((uint32_t)((float)h * (float)max_size / (float)w), 1u);
+  } else {
+    nw = std::max<uint32_t>((uint32_t)((float)w * (float)max_size / (float)h), 1u);
+    nh = max_size;
+  }
+  if (ow) *ow = nw;
+  if (oh) *oh = nh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage launchers (device pointers)
+
+static cudaStream_t pick_stream(kmg_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+static int launch_convert(kmg_ctx* ctx, const uint8_t* d_rgba, uint64_t n, int cs, float* d_work, cudaStream_t s) {
+  int grid = grid_for(ctx, n, 256, 8);
+  k_convert<<<grid, 256, 0, s>>>((const uint32_t*)d_rgba, n, cs, ctx->d_lut, (float4*)d_work);
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  return KMG_OK;
+}
+static int launch_resize(kmg_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint8_t* dst, uint32_t dw,
+                         uint32_t dh, cudaStream_t s) {
+  int grid = grid_for(ctx, (unsigned long long)dw * dh, 256, 8);
+  k_resize<<<grid, 256, 0, s>>>((const uint32_t*)src, sw, sh, (uint32_t*)dst, dw, dh);
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  return KMG_OK;
+}
+static int launch_prepare(kmg_job* j, bool palette, cudaStream_t s) {
+  k_prepare<<<1, 256, 0, s>>>(j->P, j->color_space, palette ? 1 : 0);
+  LAUNCHED(j->ctx);
+  CHECK_LAUNCH();
+  return KMG_OK;
+}
+
+static int launch_lloyd(kmg_job* j, cudaStream_t s) {
+  kmg_ctx* ctx = j->ctx;
+  const unsigned long long n = (unsigned long long)j->w * j->h;
+  const int partial = (j->sharded && ctx->n_ranks > 1) ? 1 : 0;
+  if (j->k <= 8) {
+    int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
+    k_lloyd_private<8, 256, 4><<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+  } else if (j->k <= 16) {
+    int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private16);
+    k_lloyd_private<16, 256, 4><<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+  } else if (j->k <= 32) {
+    int grid = grid_for(ctx, n, 128 * 4, ctx->occ_private32);
+    k_lloyd_private<32, 128, 4><<<grid, 128, 32 * 128 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+  } else {
+    size_t smem = (size_t)pad32(j->k) * sizeof(CentRec);
+    int grid = grid_for(ctx, n, 256 * 4, smem > 96 * 1024 ? 1 : 2);
+    k_lloyd_global<256, 4><<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial);
+  }
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+#if KMG_HAVE_NCCL_HEADER
+  if (partial) {
+    NC(nccl_api().AllReduce(j->P.acc, j->P.acc, (size_t)j->k * 4, ncclInt64, ncclSum, ctx->comm, s));
+    k_finalize<<<1, 256, 0, s>>>(j->P, j->color_space);
+    LAUNCHED(ctx);
+    CHECK_LAUNCH();
+  }
+#endif
+  return KMG_OK;
+}
+
+template <int MODE>
+static int launch_remap_mode(kmg_job* j, const uint8_t* d_rgba, uint32_t w, unsigned long long n, uint8_t* d_out,
+                             cudaStream_t s) {
+  kmg_ctx* ctx = j->ctx;
+  const unsigned long long groups = (n + 3) / 4;
+  const uint32_t* in = (const uint32_t*)d_rgba;
+  uint32_t* out = (uint32_t*)d_out;
+  if (j->k <= 8) {
+    int grid = grid_for(ctx, groups, 256, 4);
+    k_remap<MODE, 8, 256><<<grid, 256, 8 * 36, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+  } else if (j->k <= 16) {
+    int grid = grid_for(ctx, groups, 256, 4);
+    k_remap<MODE, 16, 256><<<grid, 256, 16 * 36, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+  } else if (j->k <= 32) {
+    int grid = grid_for(ctx, groups, 256, 4);
+    k_remap<MODE, 32, 256><<<grid, 256, 32 * 36, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+  } else {
+    size_t smem = (size_t)pad32(j->k) * 36;
+    int grid = grid_for(ctx, groups, 256, smem > 96 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
+    k_remap<MODE, 0, 256><<<grid, 256, smem, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+  }
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  return KMG_OK;
+}
+
+static int launch_remap(kmg_job* j, const uint8_t* d_rgba, uint32_t w, uint32_t h, int mode, uint8_t* d_out,
+                        cudaStream_t s) {
+  const unsigned long long n = (unsigned long long)w * h;
+  TRY(launch_prepare(j, true, s));
+  if (mode == KMG_REPLACE) return launch_remap_mode<0>(j, d_rgba, w, n, d_out, s);
+  if (mode == KMG_DITHER) return launch_remap_mode<1>(j, d_rgba, w, n, d_out, s);
+  if (mode == KMG_MELD) {
+    int grid = grid_for(j->ctx, n, 256, 8);
+    k_remap_meld<<<grid, 256, (size_t)j->k * 16, s>>>(j->P, (const uint32_t*)d_rgba, n, j->color_space, j->ctx->d_lut,
+                                                      (uint32_t*)d_out);
+    LAUNCHED(j->ctx);
+    CHECK_LAUNCH();
+    return KMG_OK;
+  }
+  return fail(KMG_ERR_BAD_ARG, "unknown reduce mode %d", mode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// jobs
+
+static int validate_dims(uint32_t w, uint32_t h, uint32_t k) {
+  if (w == 0 || h == 0) return fail(KMG_ERR_BAD_ARG, "image is empty (%ux%u)", w, h);
+  if ((unsigned long long)w * h >= (1ull << 32)) return fail(KMG_ERR_BAD_ARG, "image has >= 2^32 pixels (%ux%u)", w, h);
+  if (k == 0) return fail(KMG_ERR_BAD_ARG, "k must be at least 1");
+  if (k > (uint32_t)MAX_K) return fail(KMG_ERR_UNSUPPORTED, "k = %u exceeds the supported maximum of %d", k, MAX_K);
+  return KMG_OK;
+}
+
+// Initialise a job over caller-provided storage (blob of job_blob_bytes(k), optional dmin plane).
+static int job_setup(kmg_job* j, kmg_ctx* ctx, const float* d_work, uint32_t w, uint32_t h, uint32_t k, int cs,
+                     const kmg_opts& o, void* blob, float* dmin, JobState* h_state, cudaStream_t s) {
+  j->ctx = ctx;
+  j->work = (const float4*)d_work;
+  j->w = w;
+  j->h = h;
+  j->k = k;
+  j->color_space = cs;
+  j->opts = o;
+  j->blob = blob;
+  j->dmin = dmin;
+  j->h_state = h_state;
+  job_carve(j, blob);
+  CU(cudaMemsetAsync(blob, 0, job_blob_bytes(k), s));
+  JobState st;
+  memset(&st, 0, sizeof(st));
+  st.k = k;
+  st.max_iter = o.max_iter ? o.max_iter : 1;
+  st.check_every = o.check_every;
+  st.conv_threshold = o.convergence >= 0.0f ? o.convergence : (cs == KMG_LAB ? 1.0f : 0.01f);  // lib.rs:189-194
+  *h_state = st;
+  CU(cudaMemcpyAsync(j->P.st, h_state, sizeof(JobState), cudaMemcpyHostToDevice, s));
+  return KMG_OK;
+}
+
+static int job_read_state(kmg_job* j, cudaStream_t s) {
+  CU(cudaMemcpyAsync(j->h_state, j->P.st, sizeof(JobState), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+#if KMG_HAVE_NCCL_HEADER
+// Distributed init: share the colour of a globally chosen pixel (exactly one rank contributes
+// non-zero values, so the float sum is exact).
+static int share_colour(kmg_job* j, unsigned int slot, cudaStream_t s) {
+  kmg_ctx* ctx = j->ctx;
+  NC(nccl_api().AllReduce(j->d_xfer, j->d_xfer, 4, ncclFloat32, ncclSum, ctx->comm, s));
+  CU(cudaMemcpyAsync(j->P.cent + slot, j->d_xfer, 16, cudaMemcpyDeviceToDevice, s));
+  return KMG_OK;
+}
+#endif
+
+static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cudaStream_t s) {
+  kmg_ctx* ctx = j->ctx;
+  const unsigned long long n = (unsigned long long)j->w * j->h;
+  const bool dist = j->sharded && ctx->n_ranks > 1;
+  const uint32_t gw = j->sharded ? j->global_w : j->w;
+  const uint32_t gh = j->sharded ? j->global_h : j->h;
+  const unsigned long long offset = j->sharded ? (unsigned long long)j->row_offset * gw : 0ull;
+  // plus_plus_init.wgsl:161-167 — seed pixel on the clustered image
+  int64_t sx = j->opts.seed_x >= 0 ? j->opts.seed_x : (int64_t)(int32_t)((float)gw * j->opts.seed_x_frac);
+  int64_t sy = j->opts.seed_y >= 0 ? j->opts.seed_y : (int64_t)(int32_t)((float)gh * j->opts.seed_y_frac);
+  if (sx < 0 || sy < 0 || sx >= (int64_t)gw || sy >= (int64_t)gh)
+    return fail(KMG_ERR_BAD_ARG, "seed pixel (%lld,%lld) outside the %ux%u image", (long long)sx, (long long)sy, gw, gh);
+  const unsigned long long seed = (unsigned long long)sy * gw + (unsigned long long)sx;
+  const bool seed_local = seed >= offset && seed - offset < n;
+  if (!j->dmin) return fail(KMG_ERR_BAD_ARG, "job has no distance plane");
+#if KMG_HAVE_NCCL_HEADER
+  if (dist) CU(cudaMemsetAsync(j->d_xfer, 0, 16, s));
+#endif
+  k_init_seed<<<1, 32, 0, s>>>(j->P, j->work, seed_local ? seed - offset : 0ull, seed_local ? 1 : 0);
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+#if KMG_HAVE_NCCL_HEADER
+  if (dist) {
+    if (seed_local) CU(cudaMemcpyAsync(j->d_xfer, j->P.cent, 16, cudaMemcpyDeviceToDevice, s));
+    TRY(share_colour(j, 0, s));
+  }
+#endif
+  const int grid = grid_for(ctx, n, 256 * 4, 8);
+  for (uint32_t c = 1; c < j->k; ++c) {
+    if (c == 1)
+      k_init_round<true><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c);
+    else
+      k_init_round<false><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c);
+    LAUNCHED(ctx);
+    CHECK_LAUNCH();
+#if KMG_HAVE_NCCL_HEADER
+    if (dist) {
+      NC(nccl_api().AllReduce(j->P.keys + c, j->P.keys + c, 1, ncclUint64, ncclMax, ctx->comm, s));
+      CU(cudaMemsetAsync(j->d_xfer, 0, 16, s));
+      CU(cudaMemsetAsync(j->P.cent + c, 0, 16, s));
+    }
+#endif
+    k_init_pick<<<1, 32, 0, s>>>(j->P, j->work, n, offset, c);
+    LAUNCHED(ctx);
+    CHECK_LAUNCH();
+#if KMG_HAVE_NCCL_HEADER
+    if (dist) {
+      CU(cudaMemcpyAsync(j->d_xfer, j->P.cent + c, 16, cudaMemcpyDeviceToDevice, s));
+      TRY(share_colour(j, c, s));
+    }
+#endif
+  }
+  TRY(launch_prepare(j, false, s));
+  if (pick_index || pick_dist) {
+    std::vector<unsigned long long> keys(j->k);
+    CU(cudaMemcpyAsync(keys.data(), j->P.keys, (size_t)j->k * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (uint32_t c = 0; c < j->k; ++c) {
+      unsigned long long key = keys[c];
+      uint32_t bits = (uint32_t)(key >> 32);
+      float d;
+      memcpy(&d, &bits, 4);
+      if (pick_index) pick_index[c] = c == 0 ? (uint32_t)seed : (uint32_t)((key >> 32) == 0 ? 0 : ((key & 0xffffffffull) ^ 15ull));
+      if (pick_dist) pick_dist[c] = c == 0 ? 0.0f : d;
+    }
+  }
+  return KMG_OK;
+}
+
+// core/src/modules.rs:763-840.  Passes are enqueued up to the next iteration at which the
+// reference tests convergence; only then is the 64-byte state read back.
+static int job_run_impl(kmg_job* j, uint32_t* passes_out, cudaStream_t s) {
+  const uint32_t max_iter = j->opts.max_iter ? j->opts.max_iter : 1;
+  const uint32_t every = j->opts.check_every;
+  uint32_t it = 0;
+  while (it < max_iter) {
+    uint32_t stop = max_iter - 1;  // last iteration index of this chunk
+    if (every != 0) {
+      uint32_t next_check = it == 0 ? every : ((it + every - 1) / every) * every;
+      if (next_check == 0) next_check = every;
+      stop = std::min(stop, next_check);
+    }
+    for (; it <= stop; ++it) TRY(launch_lloyd(j, s));
+    TRY(job_read_state(j, s));
+    if (j->h_state->done) break;
+  }
+  if (passes_out) *passes_out = j->h_state->passes;
+  return KMG_OK;
+}
+
+extern "C" int kmg_job_create(kmg_ctx* ctx, const float* d_work, uint32_t w, uint32_t h, uint32_t k, int cs,
+                              const kmg_opts* opts, kmg_job** out) {
+  if (!ctx || !d_work || !out) return fail(KMG_ERR_BAD_ARG, "kmg_job_create: NULL argument");
+  TRY(validate_dims(w, h, k));
+  if (cs != KMG_LAB && cs != KMG_RGB) return fail(KMG_ERR_BAD_ARG, "unknown colour space %d", cs);
+  CU(cudaSetDevice(ctx->device));
+  kmg_job* j = new kmg_job();
+  void* blob = nullptr;
+  float* dmin = nullptr;
+  JobState* hs = nullptr;
+  if (cudaMalloc(&blob, job_blob_bytes(k)) != cudaSuccess || cudaMalloc((void**)&dmin, (size_t)w * h * 4) != cudaSuccess ||
+      cudaMallocHost((void**)&hs, sizeof(JobState)) != cudaSuccess) {
+    cudaGetLastError();
+    if (blob) cudaFree(blob);
+    if (dmin) cudaFree(dmin);
+    delete j;
+    return fail(KMG_ERR_OOM, "kmg_job_create: allocation failed");
+  }
+  j->owns_blob = j->owns_dmin = j->owns_h_state = true;
+  int r = job_setup(j, ctx, d_work, w, h, k, cs, resolve_opts(opts), blob, dmin, hs, ctx->stream);
+  if (r == KMG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) r = fail(KMG_ERR_CUDA, "job setup failed");
+  if (r != KMG_OK) {
+    kmg_job_destroy(j);
+    return r;
+  }
+  *out = j;
+  return KMG_OK;
+}
+
+extern "C" void kmg_job_destroy(kmg_job* j) {
+  if (!j) return;
+  cudaSetDevice(j->ctx->device);
+  if (j->owns_blob && j->blob) cudaFree(j->blob);
+  if (j->owns_dmin && j->dmin) cudaFree(j->dmin);
+  if (j->owns_h_state && j->h_state) cudaFreeHost(j->h_state);
+  delete j;
+}
+
+extern "C" int kmg_job_set_shard(kmg_job* j, uint32_t gw, uint32_t gh, uint32_t row_offset) {
+  if (!j) return fail(KMG_ERR_BAD_ARG, "kmg_job_set_shard: NULL job");
+  if (gw != j->w || (unsigned long long)row_offset + j->h > gh)
+    return fail(KMG_ERR_BAD_ARG, "shard rows [%u,%u) of width %u do not fit the %ux%u image", row_offset,
+                row_offset + j->h, j->w, gw, gh);
+  j->sharded = true;
+  j->global_w = gw;
+  j->global_h = gh;
+  j->row_offset = row_offset;
+  return KMG_OK;
+}
+
+extern "C" int kmg_job_init(kmg_job* j, uint32_t* pick_index, float* pick_dist, void* stream) {
+  if (!j) return fail(KMG_ERR_BAD_ARG, "kmg_job_init: NULL job");
+  CU(cudaSetDevice(j->ctx->device));
+  return job_init_impl(j, pick_index, pick_dist, pick_stream(j->ctx, stream));
+}
+
+extern "C" int kmg_job_set_centroids(kmg_job* j, const float* c, void* stream) {
+  if (!j || !c) return fail(KMG_ERR_BAD_ARG, "kmg_job_set_centroids: NULL argument");
+  CU(cudaSetDevice(j->ctx->device));
+  cudaStream_t s = pick_stream(j->ctx, stream);
+  CU(cudaMemcpyAsync(j->P.cent, c, (size_t)j->k * 16, cudaMemcpyHostToDevice, s));
+  TRY(launch_prepare(j, false, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_job_get_centroids(kmg_job* j, float* c, void* stream) {
+  if (!j || !c) return fail(KMG_ERR_BAD_ARG, "kmg_job_get_centroids: NULL argument");
+  CU(cudaSetDevice(j->ctx->device));
+  cudaStream_t s = pick_stream(j->ctx, stream);
+  CU(cudaMemcpyAsync(c, j->P.cent, (size_t)j->k * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_job_step(kmg_job* j, uint32_t count, void* stream) {
+  if (!j) return fail(KMG_ERR_BAD_ARG, "kmg_job_step: NULL job");
+  CU(cudaSetDevice(j->ctx->device));
+  cudaStream_t s = pick_stream(j->ctx, stream);
+  for (uint32_t i = 0; i < count; ++i) TRY(launch_lloyd(j, s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_job_run(kmg_job* j, uint32_t* passes_out, void* stream) {
+  if (!j) return fail(KMG_ERR_BAD_ARG, "kmg_job_run: NULL job");
+  CU(cudaSetDevice(j->ctx->device));
+  return job_run_impl(j, passes_out, pick_stream(j->ctx, stream));
+}
+
+extern "C" int kmg_job_stats(kmg_job* j, uint32_t* conv, uint32_t* passes, uint64_t* slow, void* stream) {
+  if (!j) return fail(KMG_ERR_BAD_ARG, "kmg_job_stats: NULL job");
+  CU(cudaSetDevice(j->ctx->device));
+  TRY(job_read_state(j, pick_stream(j->ctx, stream)));
+  if (conv) *conv = j->h_state->conv;
+  if (passes) *passes = j->h_state->passes;
+  if (slow) *slow = j->h_state->slow_pixels;
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident stage entry points
+
+extern "C" int kmg_dev_convert(kmg_ctx* ctx, const uint8_t* d_rgba, uint64_t n, int cs, float* d_work, void* stream) {
+  if (!ctx || !d_rgba || !d_work) return fail(KMG_ERR_BAD_ARG, "kmg_dev_convert: NULL argument");
+  if (n == 0) return fail(KMG_ERR_BAD_ARG, "kmg_dev_convert: empty input");
+  CU(cudaSetDevice(ctx->device));
+  return launch_convert(ctx, d_rgba, n, cs, d_work, pick_stream(ctx, stream));
+}
+
+extern "C" int kmg_dev_resize(kmg_ctx* ctx, const uint8_t* d_src, uint32_t sw, uint32_t sh, uint8_t* d_dst,
+                              uint32_t dw, uint32_t dh, void* stream) {
+  if (!ctx || !d_src || !d_dst) return fail(KMG_ERR_BAD_ARG, "kmg_dev_resize: NULL argument");
+  if (!sw || !sh || !dw || !dh) return fail(KMG_ERR_BAD_ARG, "kmg_dev_resize: empty image");
+  CU(cudaSetDevice(ctx->device));
+  return launch_resize(ctx, d_src, sw, sh, d_dst, dw, dh, pick_stream(ctx, stream));
+}
+
+// A throw-away job over fixed centroids (remap / assign with host-provided centroids).
+struct TempJob {
+  kmg_job job;
+  void* blob = nullptr;
+  JobState* hs = nullptr;
+  ~TempJob() {
+    if (blob) cudaFree(blob);
+    if (hs) cudaFreeHost(hs);
+  }
+  int setup(kmg_ctx* ctx, uint32_t w, uint32_t h, const float* cent_host, uint32_t k, int cs, cudaStream_t s) {
+    CU(cudaMalloc(&blob, job_blob_bytes(k)));
+    CU(cudaMallocHost((void**)&hs, sizeof(JobState)));
+    kmg_opts o;
+    kmg_default_opts(&o);
+    TRY(job_setup(&job, ctx, nullptr, w, h, k, cs, o, blob, nullptr, hs, s));
+    // fixed centroids: force w = 1.0 like CentroidsBuffer::fixed_centroids (structures.rs:536,540)
+    std::vector<float> c(cent_host, cent_host + (size_t)k * 4);
+    CU(cudaMemcpyAsync(job.P.cent, c.data(), (size_t)k * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));  // c goes out of scope
+    return KMG_OK;
+  }
+};
+
+extern "C" int kmg_dev_assign(kmg_ctx* ctx, const float* d_work, uint64_t n, const float* cent, uint32_t k,
+                              uint32_t* d_labels, void* stream) {
+  if (!ctx || !d_work || !cent || !d_labels) return fail(KMG_ERR_BAD_ARG, "kmg_dev_assign: NULL argument");
+  if (n == 0 || n >= (1ull << 32)) return fail(KMG_ERR_BAD_ARG, "kmg_dev_assign: bad pixel count");
+  TRY(validate_dims(1, 1, k));
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  TempJob t;
+  TRY(t.setup(ctx, (uint32_t)n, 1, cent, k, KMG_LAB, s));
+  TRY(launch_prepare(&t.job, false, s));
+  size_t smem = (size_t)pad32(k) * sizeof(CentRec);
+  int grid = grid_for(ctx, n, 256 * 4, smem > 96 * 1024 ? 1 : 2);
+  k_assign<256, 4><<<grid, 256, smem, s>>>(t.job.P, (const float4*)d_work, n, d_labels);
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_dev_remap(kmg_ctx* ctx, const uint8_t* d_rgba, uint32_t w, uint32_t h, const float* cent,
+                             uint32_t k, int cs, int mode, uint8_t* d_out, void* stream) {
+  if (!ctx || !d_rgba || !cent || !d_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_remap: NULL argument");
+  TRY(validate_dims(w, h, k));
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  TempJob t;
+  TRY(t.setup(ctx, w, h, cent, k, cs, s));
+  TRY(launch_remap(&t.job, d_rgba, w, h, mode, d_out, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_dev_remap_job(kmg_ctx* ctx, const uint8_t* d_rgba, uint32_t w, uint32_t h, kmg_job* job, int mode,
+                                 uint8_t* d_out, void* stream) {
+  if (!ctx || !d_rgba || !job || !d_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_remap_job: NULL argument");
+  TRY(validate_dims(w, h, job->k));
+  CU(cudaSetDevice(ctx->device));
+  return launch_remap(job, d_rgba, w, h, mode, d_out, pick_stream(ctx, stream));
+}
+
+extern "C" int kmg_dev_synth(kmg_ctx* ctx, uint8_t* d_rgba, uint64_t first, uint64_t n, uint32_t frame, uint32_t seed,
+                             uint32_t blobs, void* stream) {
+  if (!ctx || !d_rgba || n == 0) return fail(KMG_ERR_BAD_ARG, "kmg_dev_synth: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int grid = grid_for(ctx, n, 256, 8);
+  k_synth<<<grid, 256, 0, pick_stream(ctx, stream)>>>((uint32_t*)d_rgba, first, n, frame, seed, blobs);
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  return KMG_OK;
+}
+
+extern "C" int kmg_dev_srgb_table(kmg_ctx* ctx, float* table_out) {
+  if (!ctx || !table_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_srgb_table: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpy(table_out, ctx->d_lut, 256 * sizeof(float), cudaMemcpyDeviceToHost));
+  return KMG_OK;
+}
+
+extern "C" int kmg_dev_fast_lab_error(kmg_ctx* ctx, float* max_err_out) {
+  if (!ctx || !max_err_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_fast_lab_error: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, 4));
+  CU(cudaMemsetAsync(d, 0, 4, ctx->stream));
+  k_fast_lab_error<<<ctx->sms * 8, 256, 0, ctx->stream>>>(ctx->d_lut, d);
+  LAUNCHED(ctx);
+  cudaError_t e = cudaMemcpyAsync(max_err_out, d, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(KMG_ERR_CUDA, "kmg_dev_fast_lab_error: %s", cudaGetErrorString(e));
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-means on a device-resident RGBA8 image using workspace storage.
+// operations::extract_palette_kmeans (core/src/operations.rs:15-88).
+
+static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, uint32_t w, uint32_t h, uint32_t k,
+                            int cs, const kmg_opts& o, kmg_job* job, uint32_t* passes_out) {
+  cudaStream_t s = ws->stream;
+  const uint8_t* img = d_rgba;
+  uint32_t iw = w, ih = h;
+  if (o.max_dim != 0 && (w > o.max_dim || h > o.max_dim)) {  // structures.rs:67-74
+    kmg_resized_dims(w, h, o.max_dim, &iw, &ih);
+    TRY(ws->small.ensure((size_t)iw * ih * 4));
+    TRY(launch_resize(ctx, d_rgba, w, h, (uint8_t*)ws->small.p, iw, ih, s));
+    img = (const uint8_t*)ws->small.p;
+  }
+  const size_t n = (size_t)iw * ih;
+  TRY(ws->work.ensure(n * 16));
+  TRY(ws->dmin.ensure(n * 4));
+  TRY(ws->blob.ensure(job_blob_bytes(k)));
+  TRY(launch_convert(ctx, img, n, cs, (float*)ws->work.p, s));
+  TRY(job_setup(job, ctx, (const float*)ws->work.p, iw, ih, k, cs, o, ws->blob.p, (float*)ws->dmin.p, ws->h_state, s));
+  TRY(job_init_impl(job, nullptr, nullptr, s));
+  TRY(job_run_impl(job, passes_out, s));
+  return KMG_OK;
+}
+
+static int check_image_args(const char* fn, kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t k,
+                            int cs) {
+  if (!ctx) return fail(KMG_ERR_BAD_ARG, "%s: ctx is NULL", fn);
+  if (!rgba) return fail(KMG_ERR_BAD_ARG, "%s: image pointer is NULL", fn);
+  if (cs != KMG_LAB && cs != KMG_RGB) return fail(KMG_ERR_BAD_ARG, "%s: unknown colour space %d", fn, cs);
+  return validate_dims(w, h, k);
+}
+
+extern "C" int kmg_kmeans_palette(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t k, int cs,
+                                  const kmg_opts* opts, float* centroids_out, uint32_t* passes_out) {
+  TRY(check_image_args("kmg_kmeans_palette", ctx, rgba, w, h, k, cs));
+  if (!centroids_out) return fail(KMG_ERR_BAD_ARG, "kmg_kmeans_palette: centroids_out is NULL");
+  CU(cudaSetDevice(ctx->device));
+  Workspace* ws = ws_acquire(ctx);
+  if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
+  WsGuard guard{ctx, ws};
+  const size_t bytes = (size_t)w * h * 4;
+  TRY(ws->in.ensure(bytes));
+  CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, ws->stream));
+  kmg_job job;
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, passes_out));
+  CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, ws->stream));
+  CU(cudaStreamSynchronize(ws->stream));
+  return KMG_OK;
+}
+
+extern "C" int kmg_remap(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, const float* centroids, uint32_t k,
+                         int cs, int mode, uint8_t* out_rgba) {
+  TRY(check_image_args("kmg_remap", ctx, rgba, w, h, k, cs));
+  if (!centroids || !out_rgba) return fail(KMG_ERR_BAD_ARG, "kmg_remap: NULL argument");
+  if (mode < KMG_REPLACE || mode > KMG_MELD) return fail(KMG_ERR_BAD_ARG, "kmg_remap: unknown mode %d", mode);
+  CU(cudaSetDevice(ctx->device));
+  Workspace* ws = ws_acquire(ctx);
+  if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
+  WsGuard guard{ctx, ws};
+  cudaStream_t s = ws->stream;
+  const size_t bytes = (size_t)w * h * 4;
+  TRY(ws->in.ensure(bytes));
+  TRY(ws->out.ensure(bytes));
+  TRY(ws->blob.ensure(job_blob_bytes(k)));
+  CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, s));
+  kmg_job job;
+  kmg_opts o;
+  kmg_default_opts(&o);
+  TRY(job_setup(&job, ctx, nullptr, w, h, k, cs, o, ws->blob.p, nullptr, ws->h_state, s));
+  CU(cudaMemcpyAsync(job.P.cent, centroids, (size_t)k * 16, cudaMemcpyHostToDevice, s));
+  TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, h, mode, (uint8_t*)ws->out.p, s));
+  CU(cudaMemcpyAsync(out_rgba, ws->out.p, bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_reduce(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t k, int cs, int mode,
+                          const kmg_opts* opts, uint8_t* out_rgba, float* centroids_out, uint32_t* passes_out) {
+  TRY(check_image_args("kmg_reduce", ctx, rgba, w, h, k, cs));
+  if (!out_rgba) return fail(KMG_ERR_BAD_ARG, "kmg_reduce: out_rgba is NULL");
+  if (mode < KMG_REPLACE || mode > KMG_MELD) return fail(KMG_ERR_BAD_ARG, "kmg_reduce: unknown mode %d", mode);
+  CU(cudaSetDevice(ctx->device));
+  Workspace* ws = ws_acquire(ctx);
+  if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
+  WsGuard guard{ctx, ws};
+  cudaStream_t s = ws->stream;
+  const size_t bytes = (size_t)w * h * 4;
+  TRY(ws->in.ensure(bytes));
+  TRY(ws->out.ensure(bytes));
+  CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, s));
+  kmg_job job;
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, passes_out));
+  TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, h, mode, (uint8_t*)ws->out.p, s));
+  CU(cudaMemcpyAsync(out_rgba, ws->out.p, bytes, cudaMemcpyDeviceToHost, s));
+  if (centroids_out) CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+extern "C" int kmg_resize(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t max_size, uint8_t* out) {
+  TRY(check_image_args("kmg_resize", ctx, rgba, w, h, 1, KMG_LAB));
+  if (!out || max_size == 0) return fail(KMG_ERR_BAD_ARG, "kmg_resize: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  Workspace* ws = ws_acquire(ctx);
+  if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
+  WsGuard guard{ctx, ws};
+  uint32_t dw, dh;
+  kmg_resized_dims(w, h, max_size, &dw, &dh);
+  const size_t bytes = (size_t)w * h * 4, obytes = (size_t)dw * dh * 4;
+  TRY(ws->in.ensure(bytes));
+  TRY(ws->small.ensure(obytes));
+  CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, ws->stream));
+  TRY(launch_resize(ctx, (const uint8_t*)ws->in.p, w, h, (uint8_t*)ws->small.p, dw, dh, ws->stream));
+  CU(cudaMemcpyAsync(out, ws->small.p, obytes, cudaMemcpyDeviceToHost, ws->stream));
+  CU(cudaStreamSynchronize(ws->stream));
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batches of frames (BASELINE config 5)
+
+extern "C" int kmg_dev_reduce_batch(kmg_ctx* ctx, const uint8_t* d_rgba, uint32_t n_frames, uint32_t w, uint32_t h,
+                                    uint32_t k, int cs, int mode, const kmg_opts* opts, uint8_t* d_out,
+                                    float* centroids_out, uint32_t* passes_out, void* stream) {
+  TRY(check_image_args("kmg_dev_reduce_batch", ctx, d_rgba, w, h, k, cs));
+  if (!d_out || n_frames == 0) return fail(KMG_ERR_BAD_ARG, "kmg_dev_reduce_batch: bad argument");
+  if (mode < KMG_REPLACE || mode > KMG_MELD) return fail(KMG_ERR_BAD_ARG, "kmg_dev_reduce_batch: unknown mode %d", mode);
+  (void)stream;
+  CU(cudaSetDevice(ctx->device));
+  Workspace* ws = ws_acquire(ctx);
+  if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
+  WsGuard guard{ctx, ws};
+  const kmg_opts o = resolve_opts(opts);
+  const size_t frame_bytes = (size_t)w * h * 4;
+  for (uint32_t f = 0; f < n_frames; ++f) {
+    kmg_job job;
+    uint32_t passes = 0;
+    const uint8_t* in = d_rgba + (size_t)f * frame_bytes;
+    TRY(kmeans_on_device(ctx, ws, in, w, h, k, cs, o, &job, &passes));
+    TRY(launch_remap(&job, in, w, h, mode, d_out + (size_t)f * frame_bytes, ws->stream));
+    if (centroids_out)
+      CU(cudaMemcpyAsync(centroids_out + (size_t)f * k * 4, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, ws->stream));
+    if (passes_out) passes_out[f] = passes;
+    // the workspace blob is reused by the next frame: drain before overwriting it
+    CU(cudaStreamSynchronize(ws->stream));
+  }
+  return KMG_OK;
+}
+
+extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_frames, uint32_t w, uint32_t h,
+                                uint32_t k, int cs, int mode, const kmg_opts* opts, uint8_t* out_rgba,
+                                float* centroids_out, uint32_t* passes_out) {
+  TRY(check_image_args("kmg_reduce_batch", ctx, rgba, w, h, k, cs));
+  if (!out_rgba || n_frames == 0) return fail(KMG_ERR_BAD_ARG, "kmg_reduce_batch: bad argument");
+  for (uint32_t f = 0; f < n_frames; ++f) {
+    const size_t off = (size_t)f * w * h * 4;
+    TRY(kmg_reduce(ctx, rgba + off, w, h, k, cs, mode, opts, out_rgba + off,
+                   centroids_out ? centroids_out + (size_t)f * k * 4 : nullptr, passes_out ? passes_out + f : nullptr));
+  }
+  return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU communicator
+
+extern "C" int kmg_comm_unique_id(kmg_ctx* ctx, uint8_t id_out[128]) {
+#if KMG_HAVE_NCCL_HEADER
+  if (!ctx || !id_out) return fail(KMG_ERR_BAD_ARG, "kmg_comm_unique_id: NULL argument");
+  if (!nccl_api().ok) return fail(KMG_ERR_NCCL, "NCCL could not be loaded (libnccl.so.2)");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NC(nccl_api().GetUniqueId(&id));
+  memcpy(id_out, &id, 128);
+  return KMG_OK;
+#else
+  (void)ctx;
+  (void)id_out;
+  return fail(KMG_ERR_UNSUPPORTED, "built without nccl.h");
+#endif
+}
+
+extern "C" int kmg_comm_init(kmg_ctx* ctx, const uint8_t id_in[128], int n_ranks, int rank) {
+#if KMG_HAVE_NCCL_HEADER
+  if (!ctx || !id_in) return fail(KMG_ERR_BAD_ARG, "kmg_comm_init: NULL argument");
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(KMG_ERR_BAD_ARG, "kmg_comm_init: bad rank %d of %d", rank, n_ranks);
+  if (!nccl_api().ok) return fail(KMG_ERR_NCCL, "NCCL could not be loaded (libnccl.so.2)");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->comm) return fail(KMG_ERR_BAD_ARG, "kmg_comm_init: communicator already initialised");
+  ncclUniqueId id;
+  memcpy(&id, id_in, 128);
+  NC(nccl_api().CommInitRank(&ctx->comm, n_ranks, id, rank));
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return KMG_OK;
+#else
+  (void)ctx;
+  (void)id_in;
+  (void)n_ranks;
+  (void)rank;
+  return fail(KMG_ERR_UNSUPPORTED, "built without nccl.h");
+#endif
+}
+
+extern "C" int kmg_comm_destroy(kmg_ctx* ctx) {
+#if KMG_HAVE_NCCL_HEADER
+  if (!ctx) return fail(KMG_ERR_BAD_ARG, "kmg_comm_destroy: NULL ctx");
+  if (ctx->comm) {
+    CU(cudaSetDevice(ctx->device));
+    NC(nccl_api().CommDestroy(ctx->comm));
+    ctx->comm = nullptr;
+  }
+  ctx->n_ranks = 1;
+  ctx->rank = 0;
+  return KMG_OK;
+#else
+  (void)ctx;
+  return KMG_OK;
+#endif
+}

@@ -1,0 +1,200 @@
+// kmg_math.cuh — device arithmetic for the image hot path.
+//
+// Two families:
+//   ex::   "exact" restatement of the reference shaders in IEEE binary32, every operation rounded
+//          separately (intrinsics __f*_rn are never contracted into FMAs), sqrt/div correctly
+//          rounded, pow_f32(x,y) := (float)pow((double)x,(double)y).  Bit-identical to
+//          oracle/oracle.cpp.  Used where values are stored or compared exactly (work plane,
+//          farthest-point distances, centroid finalisation, palette reversion, near-tie re-checks).
+//   fast:: algebraically reduced CIE94 score and approximate Lab, only ever used together with a
+//          certificate (score gap > error bound); when the certificate fails the caller re-evaluates
+//          the candidates with ex:: so the result is the reference's, bit for bit.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kmg {
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+namespace ex {
+
+__device__ __forceinline__ float pow_f32(float x, float y) { return (float)pow((double)x, (double)y); }
+
+// core/shaders/functions/delta_e.wgsl:1-22.  `one` supplies SC/SH (asymmetric).
+// c1 = sqrt(one.a^2 + one.b^2), c2 likewise for `second` (both evaluated exactly by the caller).
+__device__ __forceinline__ float chroma(float a, float b) { return fsqrt(fadd(fmul(a, a), fmul(b, b))); }
+
+__device__ __forceinline__ float cie94_c(float l1, float a1, float b1, float c1, float l2, float a2, float b2,
+                                         float c2) {
+  float dL = fsub(l1, l2);
+  float da = fsub(a1, a2);
+  float db = fsub(b1, b2);
+  float dC = fsub(c1, c2);
+  float dH = fsqrt(fmaxf(fsub(fadd(fmul(da, da), fmul(db, db)), fmul(dC, dC)), 0.0f));
+  float SC = fadd(1.0f, fmul(0.045f, c1));
+  float SH = fadd(1.0f, fmul(0.015f, c1));
+  float tL = fdiv(dL, 1.0f);
+  float tC = fdiv(dC, SC);
+  float tH = fdiv(dH, SH);
+  return fsqrt(fadd(fadd(fmul(tL, tL), fmul(tC, tC)), fmul(tH, tH)));
+}
+__device__ __forceinline__ float cie94(float l1, float a1, float b1, float l2, float a2, float b2) {
+  return cie94_c(l1, a1, b1, chroma(a1, b1), l2, a2, b2, chroma(a2, b2));
+}
+
+// core/shaders/converters/rgb_to_lab.wgsl:16-33 for one 8-bit channel, including the x100.
+__device__ __forceinline__ float srgb_decode100(uint32_t v) {
+  float c = fdiv((float)v, 255.0f);
+  float r = (c > 0.04045f) ? pow_f32(fdiv(fadd(c, 0.055f), 1.055f), 2.4f) : fdiv(c, 12.92f);
+  return fmul(r, 100.0f);
+}
+// core/shaders/converters/rgb_to_lab.wgsl:39-64
+__device__ __forceinline__ float lab_f(float t) {
+  if (t > 0.008856f) return pow_f32(t, 1.0f / 3.0f);
+  return fadd(fmul(7.787f, t), 16.0f / 116.0f);
+}
+// r,g,b already decoded and scaled by 100 (table lookup).
+__device__ __forceinline__ float4 lin100_to_lab(float r, float g, float b) {
+  float X = fadd(fadd(fmul(0.4124564f, r), fmul(0.3575761f, g)), fmul(0.1804375f, b));
+  float Y = fadd(fadd(fmul(0.2126729f, r), fmul(0.7151522f, g)), fmul(0.0721750f, b));
+  float Z = fadd(fadd(fmul(0.0193339f, r), fmul(0.1191920f, g)), fmul(0.9503041f, b));
+  float x = lab_f(fdiv(X, 95.0489f));
+  float y = lab_f(fdiv(Y, 100.0f));
+  float z = lab_f(fdiv(Z, 108.8840f));
+  float4 o;
+  o.x = fsub(fmul(116.0f, y), 16.0f);
+  o.y = fmul(500.0f, fsub(x, y));
+  o.z = fmul(200.0f, fsub(y, z));
+  o.w = chroma(o.y, o.z);
+  return o;
+}
+// core/shaders/converters/rgb8u_to_rgb32f.wgsl:16-17 (ColorSpace::Rgb): unorm8 load.
+__device__ __forceinline__ float4 rgb8_to_rgbf(uint32_t px) {
+  float4 o;
+  o.x = fdiv((float)(px & 255u), 255.0f);
+  o.y = fdiv((float)((px >> 8) & 255u), 255.0f);
+  o.z = fdiv((float)((px >> 16) & 255u), 255.0f);
+  o.w = chroma(o.y, o.z);
+  return o;
+}
+
+// rgba8unorm store: clamp, scale, round to nearest even.
+__device__ __forceinline__ uint32_t unorm8(float v) {
+  if (!(v > 0.0f)) return 0u;
+  if (v > 1.0f) v = 1.0f;
+  return (uint32_t)__float2int_rn(fmul(v, 255.0f));
+}
+// core/shaders/converters/lab_to_rgb.wgsl:40-66
+__device__ __forceinline__ float lab_finv(float t) {
+  float t3 = pow_f32(t, 3.0f);
+  if (t3 > 0.008856f) return t3;
+  return fdiv(fsub(t, 16.0f / 116.0f), 7.787f);
+}
+// core/shaders/converters/lab_to_rgb.wgsl:11-38
+__device__ __forceinline__ float srgb_encode(float c) {
+  if (c > 0.0031308f) return fsub(fmul(1.055f, pow_f32(c, 1.0f / 2.4f)), 0.055f);
+  return fmul(12.92f, c);
+}
+__device__ __forceinline__ uint32_t lab_to_rgba8(float L, float A, float B) {
+  float y = fdiv(fadd(L, 16.0f), 116.0f);
+  float x = fadd(fdiv(A, 500.0f), y);
+  float z = fsub(y, fdiv(B, 200.0f));
+  x = fmul(lab_finv(x), 95.0489f);
+  y = fmul(lab_finv(y), 100.0f);
+  z = fmul(lab_finv(z), 108.8840f);
+  x = fdiv(x, 100.0f);
+  y = fdiv(y, 100.0f);
+  z = fdiv(z, 100.0f);
+  float r = fadd(fadd(fmul(3.2404542f, x), fmul(-1.5371385f, y)), fmul(-0.4985314f, z));
+  float g = fadd(fadd(fmul(-0.9692660f, x), fmul(1.8760108f, y)), fmul(0.0415560f, z));
+  float b = fadd(fadd(fmul(0.0556434f, x), fmul(-0.2040259f, y)), fmul(1.0572252f, z));
+  return unorm8(srgb_encode(r)) | (unorm8(srgb_encode(g)) << 8) | (unorm8(srgb_encode(b)) << 16) | 0xFF000000u;
+}
+// core/shaders/converters/rgb32f_to_rgb8u.wgsl:16-17 (alpha component w).
+__device__ __forceinline__ uint32_t rgbf_to_rgba8(float r, float g, float b, float w) {
+  return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(w) << 24);
+}
+
+// Fixed-point unit of the centroid sums: rint(v * 2^16) (exact product, one rounding).
+__device__ __forceinline__ int to_fixed(float v) { return __float2int_rn(fmul(v, 65536.0f)); }
+
+}  // namespace ex
+
+namespace fast {
+
+// Per-pixel coefficients of the reduced CIE94 score (see DESIGN.md "assignment"):
+//   d^2(p,c) = [L^2 + C1^2/SC^2] + Lc^2 + p0*Lc + p1*C2^2 + p2*C2 + p3*ac + p4*bc
+// with p0 = -2L, p1 = 1/SC^2, p2 = 2*C1*(1/SH^2 - 1/SC^2), p3 = -2a/SH^2, p4 = -2b/SH^2,
+// using da^2 + db^2 - dC^2 = 2*(C1*C2 - a*ac - b*bc).  The bracket does not depend on c.
+struct PixCoef {
+  float p0, p1, p2, p3, p4;
+};
+__device__ __forceinline__ PixCoef pix_coef(float L, float a, float b, float C1) {
+  float SC = fmaf(0.045f, C1, 1.0f);
+  float SH = fmaf(0.015f, C1, 1.0f);
+  float rSC = __frcp_rn(SC);
+  float rSH = __frcp_rn(SH);
+  PixCoef p;
+  p.p1 = rSC * rSC;
+  float hs = rSH * rSH;
+  p.p0 = -2.0f * L;
+  p.p2 = (C1 + C1) * (hs - p.p1);
+  float t = -2.0f * hs;
+  p.p3 = t * a;
+  p.p4 = t * b;
+  return p;
+}
+// Centroid record used by the score: {Lc^2, Lc, C2^2, C2}, {ac, bc, -, -}.
+__device__ __forceinline__ float score(const PixCoef& p, float4 q0, float2 q1) {
+  float s = fmaf(p.p0, q0.y, q0.x);
+  s = fmaf(p.p1, q0.z, s);
+  s = fmaf(p.p2, q0.w, s);
+  s = fmaf(p.p3, q1.x, s);
+  s = fmaf(p.p4, q1.y, s);
+  return s;
+}
+// Absolute error bound of a score difference (rounding of the 5-term FMA chain, of the
+// coefficients, and the reference's own f32 rounding), generous by > 4x:
+//   eps = 2^-18 * [ (|L| + Lmax)^2 + 2 * (C1 + Cmax)^2 ].
+__device__ __forceinline__ float score_eps(float L, float C1, float lmax, float cmax) {
+  float u = fabsf(L) + lmax;
+  float v = C1 + cmax;
+  return 3.814697265625e-6f * fmaf(u, u, 2.0f * v * v);
+}
+
+// Approximate f(t) of xyz_to_lab: relative error <= ~2^-21.
+__device__ __forceinline__ float lab_f(float t) {
+  float lg = __log2f(t);
+  float y0 = exp2f(lg * 0.33333334f);
+  // one Newton step for the cube root, then the (1/3)_f32 vs 1/3 exponent correction
+  float r = __frcp_rn(y0 * y0);
+  float y1 = fmaf(y0, 0.6666667f, 0.33333334f * t * r);
+  y1 = y1 * fmaf(6.8862e-9f, lg, 1.0f);  // t^(0.3333333432674408 - 1/3) = 2^(9.934e-9 * log2 t)
+  float lin = fmaf(7.787f, t, 16.0f / 116.0f);
+  return t > 0.008856f ? y1 : lin;
+}
+// r,g,b decoded and scaled by 100.  Absolute error of the result <= LAB_ERR per component.
+__device__ __forceinline__ float3 lin100_to_lab(float r, float g, float b) {
+  float X = fmaf(0.1804375f, b, fmaf(0.3575761f, g, 0.4124564f * r));
+  float Y = fmaf(0.0721750f, b, fmaf(0.7151522f, g, 0.2126729f * r));
+  float Z = fmaf(0.9503041f, b, fmaf(0.1191920f, g, 0.0193339f * r));
+  float x = lab_f(X * (1.0f / 95.0489f));
+  float y = lab_f(Y * (1.0f / 100.0f));
+  float z = lab_f(Z * (1.0f / 108.8840f));
+  float3 o;
+  o.x = fmaf(116.0f, y, -16.0f);
+  o.y = 500.0f * (x - y);
+  o.z = 200.0f * (y - z);
+  return o;
+}
+// Bound on |fast Lab - exact Lab| (Euclidean norm); measured max is ~2e-4 over all 2^24 colours
+// (tests/test_gpu_parity.py::test_fast_lab_error), the bound keeps a 5x margin.
+constexpr float LAB_ERR = 1.0e-3f;
+
+}  // namespace fast
+}  // namespace kmg

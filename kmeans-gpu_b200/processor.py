@@ -1,0 +1,274 @@
+"""Host-side mirror of the reference's public API (core/src/lib.rs, core/src/image.rs).
+
+Same names, argument meaning and error behaviour as the Rust crate: `ImageProcessor.palette`,
+`.find`, `.reduce`, enums `ColorSpace`, `Algorithm`, `ReduceMode`, and `Image`.  Images are numpy
+uint8 arrays of shape (h, w, 4) (tightly packed RGBA8, as `&[RGBA8]` in the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+from ._native import KmgError, KmgOpts
+
+
+class ColorSpace(enum.IntEnum):
+    """core/src/lib.rs:168-213"""
+
+    Lab = 0
+    Rgb = 1
+
+    @staticmethod
+    def from_str(s: str) -> "ColorSpace":
+        if s == "lab":
+            return ColorSpace.Lab
+        if s == "rgb":
+            return ColorSpace.Rgb
+        raise ValueError(f"Unsupported color space {s}")
+
+    @property
+    def label(self) -> str:
+        return "lab" if self is ColorSpace.Lab else "rgb"
+
+    def convergence(self) -> float:
+        return 1.0 if self is ColorSpace.Lab else 0.01
+
+    def __str__(self) -> str:
+        return self.label
+
+
+class Algorithm(enum.Enum):
+    """core/src/lib.rs:216-232"""
+
+    Kmeans = "kmeans"
+    Octree = "octree"
+
+    def __str__(self) -> str:
+        return self.value
+
+
+class ReduceMode(enum.IntEnum):
+    """core/src/lib.rs:235-253"""
+
+    Replace = 0
+    Dither = 1
+    Meld = 2
+
+    def __str__(self) -> str:
+        return self.name.lower()
+
+
+@dataclass
+class Opts:
+    """The reference's hard-coded constants (kmg_opts in include/kmeans_gpu.h)."""
+
+    max_dim: int = 256
+    max_iter: int = 128
+    check_every: int = 8
+    convergence: float = -1.0
+    seed_x_frac: float = 0.5625
+    seed_y_frac: float = 0.93359375
+    seed_x: int = -1
+    seed_y: int = -1
+
+    def to_c(self) -> KmgOpts:
+        return KmgOpts(C.sizeof(KmgOpts), self.max_dim, self.max_iter, self.check_every, self.convergence,
+                       self.seed_x_frac, self.seed_y_frac, self.seed_x, self.seed_y)
+
+
+class Image:
+    """core/src/image.rs:20-48 — (width, height) + RGBA8 pixels."""
+
+    def __init__(self, dimensions, rgba):
+        w, h = int(dimensions[0]), int(dimensions[1])
+        arr = np.ascontiguousarray(rgba, dtype=np.uint8)
+        if arr.size != w * h * 4:
+            raise ValueError(f"pixel buffer has {arr.size} bytes, expected {w * h * 4}")
+        self.dimensions = (w, h)
+        self.rgba = arr.reshape(h, w, 4)
+
+    @staticmethod
+    def new(dimensions, rgba) -> "Image":
+        return Image(dimensions, rgba)
+
+    @staticmethod
+    def from_array(arr: np.ndarray) -> "Image":
+        arr = np.asarray(arr)
+        if arr.ndim != 3 or arr.shape[2] != 4:
+            raise ValueError("expected an (h, w, 4) uint8 array")
+        return Image((arr.shape[1], arr.shape[0]), arr)
+
+    def get_pixel(self, x: int, y: int):
+        return tuple(int(v) for v in self.rgba[y, x])
+
+    def into_raw_pixels(self) -> np.ndarray:
+        return self.rgba.reshape(-1, 4)
+
+
+def _as_image(image) -> Image:
+    return image if isinstance(image, Image) else Image.from_array(image)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def fixed_centroids(colors_rgba8, color_space: ColorSpace = ColorSpace.Lab) -> np.ndarray:
+    """CentroidsBuffer::fixed_centroids (core/src/structures.rs:523-553)."""
+    cols = np.ascontiguousarray(colors_rgba8, dtype=np.uint8).reshape(-1, 4)
+    out = np.empty((cols.shape[0], 4), np.float32)
+    _native.load().kmg_fixed_centroids(cols.ctypes.data_as(C.POINTER(C.c_uint8)), cols.shape[0], int(color_space),
+                                       out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def centroids_to_rgba8(centroids, color_space: ColorSpace = ColorSpace.Lab) -> np.ndarray:
+    """CentroidsBuffer::pull_values (core/src/structures.rs:600-617)."""
+    cent = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, 4)
+    out = np.empty((cent.shape[0], 4), np.uint8)
+    _native.load().kmg_centroids_to_rgba8(cent.ctypes.data_as(C.POINTER(C.c_float)), cent.shape[0], int(color_space),
+                                          out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out
+
+
+def sort_palette_by_lightness(colors_rgba8) -> np.ndarray:
+    """core/src/lib.rs:276-284."""
+    cols = np.ascontiguousarray(colors_rgba8, dtype=np.uint8).reshape(-1, 4).copy()
+    _native.load().kmg_sort_palette_by_lightness(cols.ctypes.data_as(C.POINTER(C.c_uint8)), cols.shape[0])
+    return cols
+
+
+def resized_dims(w: int, h: int, max_size: int = 256):
+    ow, oh = C.c_uint32(), C.c_uint32()
+    _native.load().kmg_resized_dims(w, h, max_size, C.byref(ow), C.byref(oh))
+    return ow.value, oh.value
+
+
+class ImageProcessor:
+    """core/src/lib.rs:24-165.  One instance may be shared by many threads
+    (core/examples/parallel.rs:23,36-51)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _native.load()
+        handle = C.c_void_p()
+        _native.check(self._lib.kmg_create(device, C.byref(handle)))
+        self._ctx = handle
+        self.device = device
+
+    @staticmethod
+    def new(device: int = 0) -> "ImageProcessor":
+        return ImageProcessor(device)
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.kmg_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    def launch_count(self) -> int:
+        return int(self._lib.kmg_launch_count(self._ctx))
+
+    # -- the three reference operations -------------------------------------------------------
+
+    def palette(self, color_count: int, image, algo: Algorithm = Algorithm.Kmeans, opts: Opts | None = None,
+                color_space: ColorSpace = ColorSpace.Lab) -> np.ndarray:
+        """lib.rs:67-77 + kmeans_palette :255-286: k colours (RGBA8, alpha 255) sorted by Lab L."""
+        if algo is not Algorithm.Kmeans:
+            raise KmgError(5, "Algorithm::Octree is the reference's CPU quantiser (core/src/octree.rs); "
+                              "it is outside the CUDA hot path")
+        cent, _ = self.kmeans_centroids(color_count, image, color_space, opts)
+        return sort_palette_by_lightness(centroids_to_rgba8(cent, color_space))
+
+    def find(self, image, colors, reduce_mode: ReduceMode = ReduceMode.Replace,
+             color_space: ColorSpace = ColorSpace.Lab) -> Image:
+        """lib.rs:79-114: remap onto a fixed palette given as RGBA8 colours."""
+        cent = fixed_centroids(colors, color_space)
+        return self.remap(image, cent, reduce_mode, color_space)
+
+    def reduce(self, color_count: int, image, algo: Algorithm = Algorithm.Kmeans,
+               reduce_mode: ReduceMode = ReduceMode.Replace, opts: Opts | None = None,
+               color_space: ColorSpace = ColorSpace.Lab, return_details: bool = False):
+        """lib.rs:116-164."""
+        if algo is not Algorithm.Kmeans:
+            raise KmgError(5, "Algorithm::Octree is the reference's CPU quantiser (core/src/octree.rs); "
+                              "feed its palette to find() instead")
+        img = _as_image(image)
+        w, h = img.dimensions
+        out = np.empty((h, w, 4), np.uint8)
+        cent = np.empty((int(color_count), 4), np.float32) if color_count > 0 else np.empty((0, 4), np.float32)
+        passes = C.c_uint32(0)
+        o = (opts or Opts()).to_c()
+        _native.check(self._lib.kmg_reduce(self._ctx, _ptr(img.rgba), w, h, int(color_count), int(color_space),
+                                           int(reduce_mode), C.byref(o), _ptr(out),
+                                           cent.ctypes.data_as(C.POINTER(C.c_float)), C.byref(passes)))
+        res = Image((w, h), out)
+        return (res, cent, passes.value) if return_details else res
+
+    # -- pieces of the boundary exposed for callers that keep centroids ------------------------
+
+    def kmeans_centroids(self, color_count: int, image, color_space: ColorSpace = ColorSpace.Lab,
+                         opts: Opts | None = None):
+        """operations::extract_palette_kmeans (operations.rs:15-88): raw centroids + pass count."""
+        img = _as_image(image)
+        w, h = img.dimensions
+        cent = np.empty((max(int(color_count), 0), 4), np.float32)
+        passes = C.c_uint32(0)
+        o = (opts or Opts()).to_c()
+        _native.check(self._lib.kmg_kmeans_palette(self._ctx, _ptr(img.rgba), w, h, int(color_count),
+                                                   int(color_space), C.byref(o),
+                                                   cent.ctypes.data_as(C.POINTER(C.c_float)), C.byref(passes)))
+        return cent, passes.value
+
+    def remap(self, image, centroids, reduce_mode: ReduceMode = ReduceMode.Replace,
+              color_space: ColorSpace = ColorSpace.Lab) -> Image:
+        """operations::{find_colors,dither_colors,meld_colors} (operations.rs:99-271)."""
+        img = _as_image(image)
+        w, h = img.dimensions
+        cent = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, 4)
+        out = np.empty((h, w, 4), np.uint8)
+        _native.check(self._lib.kmg_remap(self._ctx, _ptr(img.rgba), w, h, cent.ctypes.data_as(C.POINTER(C.c_float)),
+                                          cent.shape[0], int(color_space), int(reduce_mode), _ptr(out)))
+        return Image((w, h), out)
+
+    def resize(self, image, max_size: int) -> Image:
+        """InputTexture::resized (structures.rs:76-182) + pull_image."""
+        img = _as_image(image)
+        w, h = img.dimensions
+        ow, oh = resized_dims(w, h, max_size)
+        out = np.empty((oh, ow, 4), np.uint8)
+        _native.check(self._lib.kmg_resize(self._ctx, _ptr(img.rgba), w, h, max_size, _ptr(out)))
+        return Image((ow, oh), out)
+
+    def reduce_batch(self, color_count: int, frames: np.ndarray, reduce_mode: ReduceMode = ReduceMode.Replace,
+                     opts: Opts | None = None, color_space: ColorSpace = ColorSpace.Lab):
+        """Batch of equally sized frames, array (n, h, w, 4)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n, h, w, _ = frames.shape
+        out = np.empty_like(frames)
+        cent = np.empty((n, int(color_count), 4), np.float32)
+        passes = np.zeros(n, np.uint32)
+        o = (opts or Opts()).to_c()
+        _native.check(self._lib.kmg_reduce_batch(self._ctx, _ptr(frames), n, w, h, int(color_count), int(color_space),
+                                                 int(reduce_mode), C.byref(o), _ptr(out),
+                                                 cent.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 passes.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out, cent, passes
