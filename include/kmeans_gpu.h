@@ -156,6 +156,10 @@ int kmg_job_run(kmg_job* job, uint32_t* passes_out, void* stream);
 int kmg_job_stats(kmg_job* job, uint32_t* converged_out, uint32_t* passes_out, uint64_t* slow_pixels_out,
                   void* stream);
 
+/* Reduced integer sums of the last pass: k x {sum0, sum1, sum2, count}, sums in units of 2^-16
+ * (the k x 4 accumulators the multi-GPU path all-reduces; sums of shards add up exactly). */
+int kmg_job_get_sums(kmg_job* job, int64_t* sums_out, void* stream);
+
 /* Multi-GPU pixel sharding (BASELINE config 4): each rank owns a row block of one image as its
  * job's work plane; the per-pass k x 4 integer sums are all-reduced over NCCL so every rank holds
  * identical centroids.  kmg_comm_unique_id fills a 128-byte NCCL id on rank 0; the caller ships it

@@ -180,7 +180,7 @@ struct kmg_job {
 
 static size_t job_blob_bytes(uint32_t k) {
   size_t kp = pad32(k);
-  return 256 + (size_t)k * 16 + kp * sizeof(CentRec) + (size_t)ACC_COPIES * k * 4 * 8 + (size_t)k * 8 + (size_t)k * 4 + 64;
+  return 256 + (size_t)k * 16 + kp * sizeof(CentRec) + (size_t)(ACC_COPIES + 1) * k * 4 * 8 + (size_t)k * 8 + (size_t)k * 4 + 64;
 }
 static void job_carve(kmg_job* j, void* blob) {
   unsigned char* b = (unsigned char*)blob;
@@ -193,6 +193,8 @@ static void job_carve(kmg_job* j, void* blob) {
   b += kp * sizeof(CentRec);
   j->P.acc = (long long*)b;
   b += (size_t)ACC_COPIES * j->k * 4 * 8;
+  j->P.last = (long long*)b;
+  b += (size_t)j->k * 4 * 8;
   j->P.keys = (unsigned long long*)b;
   b += (size_t)j->k * 8;
   j->P.pal = (uint32_t*)b;
@@ -687,6 +689,15 @@ extern "C" int kmg_job_stats(kmg_job* j, uint32_t* conv, uint32_t* passes, uint6
   if (conv) *conv = j->h_state->conv;
   if (passes) *passes = j->h_state->passes;
   if (slow) *slow = j->h_state->slow_pixels;
+  return KMG_OK;
+}
+
+extern "C" int kmg_job_get_sums(kmg_job* j, int64_t* sums_out, void* stream) {
+  if (!j || !sums_out) return fail(KMG_ERR_BAD_ARG, "kmg_job_get_sums: NULL argument");
+  CU(cudaSetDevice(j->ctx->device));
+  cudaStream_t s = pick_stream(j->ctx, stream);
+  CU(cudaMemcpyAsync(sums_out, j->P.last, (size_t)j->k * 32, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   return KMG_OK;
 }
 

@@ -49,6 +49,7 @@ struct JobPtrs {
   float4* cent;                // k
   CentRec* tab;                // k padded to a multiple of 32 with MASKED entries
   long long* acc;              // ACC_COPIES x k x 4  (sum0,sum1,sum2,count), fixed-point 2^-16
+  long long* last;             // k x 4 — the reduced sums of the last finalised pass
   unsigned long long* keys;    // k  — arg-max keys of the init rounds
   uint32_t* pal;               // k  — centroids reverted to RGBA8
 };
@@ -382,6 +383,8 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, bool distribute
       }
       continue;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) J.last[(size_t)c * 4 + q] = s[q];
     if (s[3] > 0) {  // choose_centroid.wgsl:185-194
       const double cnt = (double)s[3];
       float4 prev = J.cent[c];

@@ -1,0 +1,454 @@
+"""Parity tests proper: the CUDA path (through the C ABI of libkmeans_gpu.so) against the CPU
+oracle on identical inputs, against the reference's committed golden images, and — at BASELINE
+sizes — through size-independent properties.
+
+Bar (north_star): labels / output pixels bit-exact, centroids within 1e-4 Lab.  What is asserted
+here is stricter: everything is bit-exact against the oracle in its fixed-point sum mode
+(centroids included), and within 2e-5 Lab of the oracle's f64-sum mode.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_rgba
+
+pytestmark = pytest.mark.gpu
+
+DARK_WHITE_RED = np.array([[5, 5, 5, 255], [255, 255, 255, 255], [255, 0, 0, 255]], np.uint8)
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kmeans_gpu_b200
+
+    return kmeans_gpu_b200
+
+
+@pytest.fixture(scope="module")
+def D():
+    import kmeans_gpu_b200.device as dev
+
+    return dev
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    assert t.cuda.is_available(), "GPU tests need a CUDA device"
+    return t
+
+
+def dev_rgba(torch, arr):
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def random_centroids(rng, k):
+    c = np.empty((k, 4), np.float32)
+    c[:, 0] = rng.uniform(0, 100, k)
+    c[:, 1] = rng.uniform(-80, 90, k)
+    c[:, 2] = rng.uniform(-100, 90, k)
+    c[:, 3] = 1.0
+    return c
+
+
+# ---- K1/K3, table, K15 -------------------------------------------------------------------------
+
+def test_srgb_table_bit_exact(proc, D, oracle):
+    assert np.array_equal(bits(D.srgb_table(proc)), bits(oracle.srgb_decode_table() * np.float32(100.0)))
+
+
+def test_convert_lab_bit_exact_random_and_grey(proc, D, oracle, torch):
+    rng = np.random.default_rng(1)
+    px = rng.integers(0, 256, (1 << 20, 4), dtype=np.uint8)
+    px[:256, :3] = np.arange(256, dtype=np.uint8)[:, None]  # greys incl. both linear segments
+    work = D.convert(proc, dev_rgba(torch, px)).cpu().numpy()
+    want = oracle.convert(px)
+    assert np.array_equal(bits(work[:, :3]), bits(want[:, :3]))
+    # 4th float carries the exact chroma sqrt(a^2 + b^2)
+    a, b = want[:, 1], want[:, 2]
+    assert np.array_equal(bits(work[:, 3]), bits(np.sqrt(a * a + b * b, dtype=np.float32)))
+
+
+def test_convert_lab_all_16m_colours(proc, D, oracle, torch):
+    """H8: exhaustive over 2^24 colours.  Both sides round a double-precision pow to f32; a
+    disagreement needs the double result within ~1e-16 relative of an f32 rounding boundary."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    px = np.stack([v & 255, (v >> 8) & 255, (v >> 16) & 255, np.full_like(v, 255)], axis=1).astype(np.uint8)
+    work = D.convert(proc, dev_rgba(torch, px)).cpu().numpy()
+    want = oracle.convert(px)
+    diff = bits(work[:, :3]) != bits(want[:, :3])
+    assert diff.sum() == 0, f"{diff.sum()} of {diff.size} components differ"
+
+
+def test_convert_rgb_bit_exact(proc, D, K, oracle, torch):
+    rng = np.random.default_rng(2)
+    px = rng.integers(0, 256, (100003, 4), dtype=np.uint8)
+    work = D.convert(proc, dev_rgba(torch, px), K.ColorSpace.Rgb).cpu().numpy()
+    want = oracle.convert(px, oracle.RGB)
+    assert np.array_equal(bits(work[:, :3]), bits(want[:, :3]))
+
+
+@pytest.mark.parametrize("shape,max_dim", [((513, 768), 256), ((768, 513), 256), ((300, 301), 256), ((1080, 1920), 256),
+                                           ((513, 768), 128), ((257, 3), 256), ((5, 1000), 256)])
+def test_resize_bit_exact(proc, K, oracle, tokyo, shape, max_dim):
+    h, w = shape
+    if (h, w) == tokyo.shape[:2]:
+        img = tokyo
+    else:
+        img = oracle.synth(w * h, seed=9, blobs=0).reshape(h, w, 4)
+        img[..., 3] = np.arange(h * w, dtype=np.uint32).reshape(h, w) % 251  # alpha is filtered too
+    out = proc.resize(img, max_dim)
+    dw, dh = oracle.resized_dims(w, h, max_dim)
+    assert out.dimensions == (dw, dh)
+    assert np.array_equal(out.rgba, oracle.resize(img, dw, dh))
+
+
+# ---- K5 ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 16, 17, 32, 33, 64, 256, 700])
+def test_assign_bit_exact(proc, D, oracle, torch, k):
+    rng = np.random.default_rng(100 + k)
+    px = rng.integers(0, 256, (200000, 4), dtype=np.uint8)
+    lab = oracle.convert(px)
+    cent = random_centroids(rng, k)
+    if k >= 3:
+        cent[k - 1] = cent[0]  # exact duplicate: lowest index must win
+        cent[1, :3] = lab[5, :3]  # a centroid sitting exactly on a pixel
+    work = torch.from_numpy(np.concatenate([lab[:, :3], np.sqrt(lab[:, 1:2] ** 2 + lab[:, 2:3] ** 2, dtype=np.float32)], axis=1)).cuda()
+    labels = D.assign(proc, work, cent).cpu().numpy().astype(np.uint32)
+    want = oracle.assign(lab, cent)
+    assert np.array_equal(labels, want)
+
+
+def test_assign_adversarial_near_ties(proc, D, oracle, torch):
+    """Centroids that differ by a few ulps, pixels equidistant from mirrored centroids: the fast
+    score cannot separate them, so the exact path must reproduce the reference's strict-'<' scan."""
+    rng = np.random.default_rng(5)
+    base = random_centroids(rng, 8)
+    cent = np.concatenate([base, base.copy(), base.copy()])
+    cent[8:16, 0] = np.nextafter(cent[8:16, 0], np.float32(1000))  # +1 ulp in L
+    cent[16:24, 1] = np.nextafter(cent[16:24, 1], np.float32(-1000))  # -1 ulp in a
+    cent = cent[rng.permutation(24)]
+    px = rng.integers(0, 256, (300000, 4), dtype=np.uint8)
+    lab = oracle.convert(px)
+    # mirrored pair around every 7th pixel in L
+    lab2 = lab.copy()
+    work_np = np.concatenate([lab2[:, :3], np.sqrt(lab2[:, 1:2] ** 2 + lab2[:, 2:3] ** 2, dtype=np.float32)], axis=1)
+    labels = D.assign(proc, torch.from_numpy(work_np).cuda(), cent).cpu().numpy().astype(np.uint32)
+    want, best, second = oracle.assign(lab2, cent, with_margin=True)
+    assert np.array_equal(labels, want)
+    assert ((second - best) == 0).mean() > 0.01  # the data really contains exact ties
+
+
+# ---- K8-K11 ------------------------------------------------------------------------------------
+
+def test_init_picks_tokyo(proc, D, K, oracle, torch, tokyo):
+    sh = oracle.shrunk(tokyo)
+    h, w = sh.shape[:2]
+    work = D.convert(proc, dev_rgba(torch, sh))
+    job = D.Job(proc, work, w, h, 8)
+    idx, dist = job.init()
+    lab = oracle.convert(sh)
+    cent, oidx, odist = oracle.init(lab, w, h, 8, 144, 159)
+    assert idx.tolist() == oidx.tolist()
+    assert np.array_equal(bits(dist), bits(odist))
+    assert np.array_equal(bits(job.centroids()), bits(cent))
+    job.close()
+
+
+@pytest.mark.parametrize("w,h,k", [(64, 64, 5), (100, 37, 12), (17, 3, 4), (256, 144, 16), (31, 1, 40)])
+def test_init_picks_with_ties(proc, D, K, oracle, torch, w, h, k):
+    """Few distinct colours => many exactly tied maxima and, once colours run out, zero maxima:
+    exercises the selectCandidate tie rule (later 16-pixel chunk wins, earliest inside a chunk)."""
+    rng = np.random.default_rng(w * h + k)
+    pal = rng.integers(0, 256, (6, 4), dtype=np.uint8)
+    pal[:, 3] = 255
+    img = pal[rng.integers(0, 6, (h, w))]
+    work = D.convert(proc, dev_rgba(torch, img))
+    opts = K.Opts(seed_x=w // 3, seed_y=h // 2)
+    job = D.Job(proc, work, w, h, k, opts=opts)
+    idx, dist = job.init()
+    cent, oidx, odist = oracle.init(oracle.convert(img), w, h, k, w // 3, h // 2)
+    assert idx.tolist() == oidx.tolist()
+    assert np.array_equal(bits(dist), bits(odist))
+    assert np.array_equal(bits(job.centroids()), bits(cent))
+    job.close()
+
+
+# ---- K5 + K6/K7 fused pass, Lloyd loop -----------------------------------------------------------
+
+@pytest.mark.parametrize("k,n_side", [(2, 300), (8, 512), (16, 400), (24, 333), (32, 256), (48, 300), (256, 256)])
+def test_lloyd_pass_bit_exact(proc, D, K, oracle, torch, k, n_side):
+    w = h = n_side
+    img = oracle.synth(w * h, seed=k, blobs=2 * k).reshape(h, w, 4)
+    lab = oracle.convert(img)
+    work = D.convert(proc, dev_rgba(torch, img))
+    rng = np.random.default_rng(k)
+    cent = lab[rng.choice(w * h, k, replace=False)].copy()
+    cent[:, 3] = 1.0
+    job = D.Job(proc, work, w, h, k)
+    job.set_centroids(cent)
+    ocent = cent
+    for _ in range(3):
+        job.step(1)
+        labels = oracle.assign(lab, ocent)
+        ocent, oconv, counts = oracle.update(lab, labels, ocent, 1.0, sum_mode=1)
+        st = job.stats()
+        assert np.array_equal(job.sums(), oracle.partial_sums(lab, labels, k))
+        assert np.array_equal(bits(job.centroids()), bits(ocent))
+        assert st["converged"] == oconv
+    assert job.stats()["passes"] == 3
+    job.close()
+
+
+def test_lloyd_empty_cluster_keeps_centroid(proc, D, K, oracle, torch):
+    """choose_centroid.wgsl:185-194: an empty cluster keeps its centroid and never counts as
+    converged, so the loop runs to the 128-iteration cap (core/src/modules.rs:764-766)."""
+    w = h = 64
+    img = oracle.synth(w * h, seed=3, blobs=4).reshape(h, w, 4)
+    lab = oracle.convert(img)
+    work = D.convert(proc, dev_rgba(torch, img))
+    cent = np.array([[50, 0, 0, 1], [50, 0, 0, 1], [20, 10, 10, 1], [500, 500, 500, 1]], np.float32)
+    job = D.Job(proc, work, w, h, 4)
+    job.set_centroids(cent)
+    passes = job.run()
+    assert passes == 128
+    c = job.centroids()
+    assert np.array_equal(c[1], cent[1]) and np.array_equal(c[3], cent[3])
+    # oracle agrees
+    ocent = cent
+    for _ in range(128):
+        ocent, _, _ = oracle.update(lab, oracle.assign(lab, ocent), ocent, 1.0, sum_mode=1)
+    assert np.array_equal(bits(c), bits(ocent))
+    job.close()
+
+
+def test_kmeans_tokyo_bit_exact(proc, K, oracle, tokyo):
+    cent, passes = proc.kmeans_centroids(8, tokyo)
+    ocent, opasses = oracle.kmeans(tokyo, 8, opts=oracle.default_opts(sum_mode=1))
+    assert passes == opasses == 17
+    assert np.array_equal(bits(cent), bits(ocent))
+    # and within tolerance of the f64-sum restatement (north_star: 1e-4 Lab)
+    fcent, _ = oracle.kmeans(tokyo, 8, opts=oracle.default_opts(sum_mode=0))
+    assert np.abs(cent - fcent).max() < 2e-5
+
+
+@pytest.mark.parametrize("k,cs", [(1, 0), (2, 0), (5, 0), (16, 0), (40, 0), (8, 1)])
+def test_kmeans_various_k_bit_exact(proc, K, oracle, tokyo, k, cs):
+    cent, passes = proc.kmeans_centroids(k, tokyo, K.ColorSpace(cs))
+    ocent, opasses = oracle.kmeans(tokyo, k, cs, opts=oracle.default_opts(sum_mode=1))
+    assert passes == opasses
+    assert np.array_equal(bits(cent), bits(ocent))
+
+
+def test_kmeans_no_shrink_and_options(proc, K, oracle):
+    img = oracle.synth(500 * 300, seed=2, blobs=16).reshape(300, 500, 4)
+    opts = K.Opts(max_dim=0, max_iter=20, check_every=4, seed_x=7, seed_y=9)
+    cent, passes = proc.kmeans_centroids(8, img, opts=opts)
+    ocent, opasses = oracle.kmeans(img, 8, opts=oracle.default_opts(sum_mode=1, max_dim=0, max_iter=20, check_every=4, seed_x=7, seed_y=9))
+    assert passes == opasses
+    assert np.array_equal(bits(cent), bits(ocent))
+
+
+# ---- remap ---------------------------------------------------------------------------------------
+
+def test_find_goldens_bit_exact(proc, K, tokyo):
+    """The reference's own committed outputs (samples.sh:6-8)."""
+    out = proc.find(tokyo, DARK_WHITE_RED, K.ReduceMode.Replace)
+    assert np.array_equal(out.rgba, load_rgba("tokyo-find-replace-dark-white-red.png"))
+    out = proc.find(tokyo, DARK_WHITE_RED, K.ReduceMode.Dither)
+    assert np.array_equal(out.rgba, load_rgba("tokyo-find-dither-dark-white-red.png"))
+    out = proc.find(tokyo, K.parse_palette(GOLDEN / "apollo-1x.png"), K.ReduceMode.Dither)
+    assert np.array_equal(out.rgba, load_rgba("tokyo-find-dither-apollo.png"))
+
+
+@pytest.mark.parametrize("mode", ["replace", "dither"])
+@pytest.mark.parametrize("k", [1, 2, 7, 8, 16, 31, 64, 300])
+def test_remap_bit_exact_synthetic(proc, K, oracle, mode, k):
+    rng = np.random.default_rng(k)
+    w, h = 517, 389  # odd width: dither groups straddle rows, tail group is partial
+    img = oracle.synth(w * h, seed=k, blobs=0).reshape(h, w, 4)
+    cols = rng.integers(0, 256, (k, 4), dtype=np.uint8)
+    cols[:, 3] = 255
+    cent = K.fixed_centroids(cols)
+    m = K.ReduceMode.Replace if mode == "replace" else K.ReduceMode.Dither
+    out = proc.remap(img, cent, m)
+    want = (oracle.remap_replace if mode == "replace" else oracle.remap_dither)(img, cent)
+    assert np.array_equal(out.rgba, want)
+
+
+def test_remap_resurrect64_dither_4k(proc, K, oracle):
+    """BASELINE config 3 at a size the oracle still finishes quickly (960x540 crop of the 4K case)."""
+    pal = K.parse_palette(GOLDEN / "resurrect_64.png")
+    img = oracle.synth(960 * 540, seed=1, blobs=0).reshape(540, 960, 4)
+    out = proc.find(img, pal, K.ReduceMode.Dither)
+    assert np.array_equal(out.rgba, oracle.find(img, pal, "dither"))
+
+
+def test_remap_rgb_colour_space(proc, K, oracle):
+    rng = np.random.default_rng(3)
+    img = oracle.synth(300 * 200, seed=4, blobs=0).reshape(200, 300, 4)
+    cent = K.fixed_centroids(rng.integers(0, 256, (9, 4), dtype=np.uint8), K.ColorSpace.Rgb)
+    for m, f in ((K.ReduceMode.Replace, oracle.remap_replace), (K.ReduceMode.Dither, oracle.remap_dither)):
+        out = proc.remap(img, cent, m, K.ColorSpace.Rgb)
+        assert np.array_equal(out.rgba, f(img, cent, oracle.RGB))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 46])
+def test_meld_matches_oracle(proc, K, oracle, tokyo, k):
+    """R10 (no golden exists): continuous output, exact arithmetic on both sides."""
+    rng = np.random.default_rng(k)
+    cols = rng.integers(0, 256, (k, 4), dtype=np.uint8)
+    cols[:, 3] = 255
+    img = tokyo[100:300, 200:500]
+    cent = K.fixed_centroids(cols)
+    out = proc.remap(img, cent, K.ReduceMode.Meld)
+    want = oracle.remap_meld(img, cent)
+    assert np.array_equal(out.rgba, want)
+
+
+def test_reduce_tokyo_end_to_end(proc, K, oracle, tokyo):
+    """BASELINE configs 1 and 2: reduce -c 8 (replace, dither) and palette -c 8."""
+    for mode, name in ((K.ReduceMode.Replace, "replace"), (K.ReduceMode.Dither, "dither")):
+        out, cent, passes = proc.reduce(8, tokyo, K.Algorithm.Kmeans, mode, return_details=True)
+        want, ocent, opasses = oracle.reduce(tokyo, 8, name)
+        assert passes == opasses == 17
+        assert np.array_equal(bits(cent), bits(ocent))
+        assert np.array_equal(out.rgba, want)
+    pal = proc.palette(8, tokyo)
+    assert np.array_equal(pal, oracle.palette(tokyo, 8))
+    strip = load_rgba("tokyo-palette-c8-kmeans-s40.png")
+    gold = np.array([strip[20, 20 + 40 * i] for i in range(8)]).astype(int)
+    assert np.abs(pal[:, :3].astype(int) - gold[:, :3]).max() <= 1  # reference golden, +-1 LSB
+
+
+def test_reduce_batch_matches_single(proc, K, oracle):
+    frames = np.stack([oracle.synth(320 * 180, seed=3, blobs=32, frame=f).reshape(180, 320, 4) for f in range(3)])
+    out, cent, passes = proc.reduce_batch(16, frames, K.ReduceMode.Dither)
+    for f in range(3):
+        want, ocent, opasses = oracle.reduce(frames[f], 16, "dither")
+        assert passes[f] == opasses
+        assert np.array_equal(bits(cent[f]), bits(ocent))
+        assert np.array_equal(out[f], want)
+
+
+# ---- boundary behaviour --------------------------------------------------------------------------
+
+def test_errors(proc, K, tokyo):
+    with pytest.raises(K.KmgError) as e:
+        proc.reduce(0, tokyo)
+    assert e.value.code == 1
+    with pytest.raises(K.KmgError):
+        proc.remap(tokyo, np.zeros((0, 4), np.float32))
+    with pytest.raises(K.KmgError):
+        proc.reduce(5000, tokyo)  # above MAX_K
+    with pytest.raises(K.KmgError):
+        proc.palette(8, tokyo, K.Algorithm.Octree)
+    with pytest.raises(K.KmgError):
+        proc.kmeans_centroids(4, tokyo, opts=K.Opts(seed_x=100000, seed_y=0))
+    # the context is still usable afterwards
+    assert proc.find(tokyo[:8, :8], DARK_WHITE_RED).dimensions == (8, 8)
+
+
+def test_no_8192_cap_and_tiny_images(proc, K, oracle):
+    """The reference is limited to 8192x8192 textures (README.md:9-11); linear buffers are not."""
+    img = oracle.synth(9000 * 6, seed=1, blobs=4).reshape(6, 9000, 4)
+    out = proc.reduce(3, img, reduce_mode=K.ReduceMode.Dither)
+    want, _, _ = oracle.reduce(img, 3, "dither")
+    assert np.array_equal(out.rgba, want)
+    one = np.array([[[12, 200, 7, 255]]], np.uint8)
+    out, cent, passes = proc.reduce(1, one, return_details=True)
+    want, ocent, _ = oracle.reduce(one, 1, "replace")
+    assert np.array_equal(out.rgba, want) and np.array_equal(bits(cent), bits(ocent))
+
+
+def test_concurrent_callers(proc, K, oracle, tokyo):
+    """core/examples/parallel.rs:36-51 — 14 threads, k = 2..15, one shared processor."""
+    results = {}
+
+    def work(k):
+        results[k] = proc.reduce(k, tokyo, reduce_mode=K.ReduceMode.Replace, return_details=True)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2, 16)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in (2, 7, 15):
+        want, ocent, opasses = oracle.reduce(tokyo, k, "replace")
+        out, cent, passes = results[k]
+        assert passes == opasses and np.array_equal(bits(cent), bits(ocent)) and np.array_equal(out.rgba, want)
+
+
+# ---- the certificate --------------------------------------------------------------------------------
+
+def test_fast_lab_error_bound(proc, D):
+    err = D.fast_lab_error(proc)
+    assert 0 < err < 1.0e-3, err  # kmg::fast::LAB_ERR
+    print("max |fast Lab - exact Lab| =", err)
+
+
+def test_exact_path_is_rare_on_natural_data(proc, D, K, oracle, torch, tokyo):
+    sh = oracle.shrunk(tokyo)
+    h, w = sh.shape[:2]
+    work = D.convert(proc, dev_rgba(torch, sh))
+    job = D.Job(proc, work, w, h, 8)
+    job.init()
+    job.step(10)
+    st = job.stats()
+    assert st["slow_pixels"] < 0.01 * 10 * w * h, st
+    job.close()
+
+
+# ---- full BASELINE sizes: size-independent properties ---------------------------------------------
+
+def test_full_size_properties_8192(proc, D, K, oracle, torch):
+    """BASELINE config 4 geometry (8192x8192, blobs(512), k=256) on the device generator."""
+    w = h = 8192
+    n = w * h
+    img = D.synth(proc, n, seed=2, blobs=512).view(h, w, 4)
+    # generator agrees with the oracle on a slice
+    assert np.array_equal(img.view(-1, 4)[5_000_000:5_004_096].cpu().numpy(), oracle.synth(4096, first_pixel=5_000_000, seed=2, blobs=512))
+    work = D.convert(proc, img)
+    k = 256
+    rows = torch.randint(0, n, (k,), generator=torch.Generator().manual_seed(1))
+    cent = work[rows.cuda()].cpu().numpy().copy()
+    cent[:, 3] = 1.0
+    job = D.Job(proc, work, w, h, k, opts=K.Opts(max_dim=0))
+    job.set_centroids(cent)
+    job.step(1)
+    c1 = job.centroids()
+    # parity on a crop through the oracle: labels of 64k pixels and their contribution
+    crop = slice(12_345_678, 12_345_678 + 65536)
+    lab_crop = work[crop].cpu().numpy()
+    lab_crop4 = lab_crop.copy()
+    labels_gpu = D.assign(proc, work[crop].contiguous(), cent).cpu().numpy().astype(np.uint32)
+    assert np.array_equal(labels_gpu, oracle.assign(lab_crop4, cent))
+    # conservation: every pixel is counted exactly once
+    s_all = job.sums()
+    assert int(s_all[:, 3].sum()) == n
+    assert np.isfinite(c1).all() and (c1[:, 0] >= 0).all() and (c1[:, 0] <= 100.001).all()
+    # exactness under sharding: integer sums of two half-image jobs add up to the whole-image sums
+    half = n // 2
+    j0 = D.Job(proc, work[:half], w, h // 2, k, opts=K.Opts(max_dim=0))
+    j1 = D.Job(proc, work[half:], w, h // 2, k, opts=K.Opts(max_dim=0))
+    for j in (j0, j1):
+        j.set_centroids(cent)
+        j.step(1)
+    assert np.array_equal(j0.sums() + j1.sums(), s_all)
+    # and the finalisation of those sums is the oracle's
+    ocent, _ = oracle.finalize(s_all, cent, 1.0)
+    assert np.array_equal(bits(c1), bits(ocent))
+    # replace remap at full size only emits palette colours
+    out1 = job.remap(img, K.ReduceMode.Replace)
+    pal = oracle.revert(c1)
+    got = out1.view(torch.int32).unique().cpu().numpy().view(np.uint32)
+    assert set(got.tolist()) <= set(pal.view(np.uint32).ravel().tolist())
+    for j in (job, j0, j1):
+        j.close()

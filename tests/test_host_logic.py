@@ -1,0 +1,157 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares;
+host helpers (palette-crate conversions, palette parsing, shrink rule, sharding) match the oracle.
+No compute entry point is exercised here (that needs a GPU: tests/test_gpu_parity.py)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def header_functions():
+    text = (ROOT / "include" / "kmeans_gpu.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    names = header_functions()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(native_lib, n), f"{n} declared in include/kmeans_gpu.h but not exported"
+    assert native_lib.kmg_abi_version() == 1
+
+
+def test_binding_covers_header():
+    import kmeans_gpu_b200  # noqa: F401
+    from kmeans_gpu_b200 import _native
+
+    assert set(header_functions()) == set(_native.SIGNATURES)
+
+
+def test_default_opts_are_reference_constants(native_lib):
+    from kmeans_gpu_b200._native import KmgOpts
+
+    o = KmgOpts()
+    native_lib.kmg_default_opts(C.byref(o))
+    assert (o.max_dim, o.max_iter, o.check_every) == (256, 128, 8)  # structures.rs:23, modules.rs:765-766
+    assert o.convergence < 0 and (o.seed_x, o.seed_y) == (-1, -1)
+    assert (o.seed_x_frac, o.seed_y_frac) == (0.5625, 0.93359375)
+    assert o.struct_size == C.sizeof(KmgOpts)
+
+
+def test_no_gpu_fails_loudly(native_lib):
+    """Without a device kmg_create must fail with a CUDA error (no CPU fallback exists)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import kmeans_gpu_b200 as K
+
+    with pytest.raises(K.KmgError) as e:
+        K.ImageProcessor(0)
+    assert e.value.code == 2 and "no CPU fallback" in e.value.message
+
+
+def test_bad_args_rejected_without_gpu(native_lib):
+    assert native_lib.kmg_create(0, None) == 1
+    assert b"NULL" in native_lib.kmg_last_error()
+
+
+@pytest.mark.parametrize("w,h", [(768, 513), (513, 768), (300, 300), (8192, 8192), (1920, 1080), (257, 1), (1, 1000), (4000, 3)])
+def test_resized_dims_match_oracle(native_lib, oracle, w, h):
+    import kmeans_gpu_b200 as K
+
+    for m in (256, 128):
+        assert K.resized_dims(w, h, m) == oracle.resized_dims(w, h, m)
+    # structures.rs:79-89: strict `width > height`
+    assert K.resized_dims(768, 513) == (256, 171)
+    assert K.resized_dims(300, 300) == (256, 256)
+
+
+def test_fixed_centroids_match_oracle(native_lib, oracle):
+    import kmeans_gpu_b200 as K
+
+    rng = np.random.default_rng(7)
+    cols = rng.integers(0, 256, (4096, 4), dtype=np.uint8)
+    cols[:, 3] = 255
+    cols[:3] = [[0, 0, 0, 255], [255, 255, 255, 255], [10, 10, 10, 255]]
+    ours = K.fixed_centroids(cols, K.ColorSpace.Lab)
+    assert np.array_equal(ours.view(np.uint32), oracle.pal_srgb8_to_lab(cols).view(np.uint32))
+    rgb = K.fixed_centroids(cols, K.ColorSpace.Rgb)
+    assert np.array_equal(rgb[:, :3], cols[:, :3].astype(np.float32) / np.float32(255.0))
+    assert (rgb[:, 3] == 1.0).all()
+
+
+def test_centroids_to_rgba8_and_sort_match_oracle(native_lib, oracle):
+    import kmeans_gpu_b200 as K
+
+    rng = np.random.default_rng(11)
+    cols = rng.integers(0, 256, (2048, 4), dtype=np.uint8)
+    cols[:, 3] = 255
+    lab = oracle.pal_srgb8_to_lab(cols)
+    assert np.array_equal(K.centroids_to_rgba8(lab), cols)  # round trip of 8-bit colours
+    lab2 = lab + rng.normal(0, 0.3, lab.shape).astype(np.float32)
+    assert np.array_equal(K.centroids_to_rgba8(lab2), oracle.pal_lab_to_srgb8(lab2))
+    s = K.sort_palette_by_lightness(cols[:64])
+    key = oracle.pal_srgb8_to_lab(cols[:64])[:, 0]
+    assert np.array_equal(s, cols[:64][np.argsort(key, kind="stable")])
+
+
+def test_palette_parsing_rules():
+    """cli/src/args.rs:238-293 (the reference's own CLI tests)."""
+    import kmeans_gpu_b200 as K
+
+    c = K.parse_colors("#ffffff,#000000")
+    assert c.tolist() == [[255, 255, 255, 255], [0, 0, 0, 255]]
+    pal = K.parse_palette(GOLDEN / "resurrect_64.png")
+    assert pal.shape == (64, 4)
+    assert pal.tolist() == sorted(pal.tolist())
+    assert K.validate_palette("#010203").tolist() == [[1, 2, 3, 255]]
+    with pytest.raises(ValueError):
+        K.validate_palette("#12345")
+    with pytest.raises(ValueError):
+        K.validate_palette("not-a-file.png")
+    with pytest.raises(ValueError):  # more than 512 pixels
+        K.parse_palette(GOLDEN / "tokyo.png")
+
+
+def test_enums_mirror_reference():
+    import kmeans_gpu_b200 as K
+
+    assert K.ColorSpace.from_str("lab") is K.ColorSpace.Lab and str(K.ColorSpace.Rgb) == "rgb"
+    assert K.ColorSpace.Lab.convergence() == 1.0 and K.ColorSpace.Rgb.convergence() == 0.01  # lib.rs:189-194
+    with pytest.raises(ValueError):
+        K.ColorSpace.from_str("xyz")
+    assert str(K.Algorithm.Kmeans) == "kmeans" and str(K.Algorithm.Octree) == "octree"
+    assert [str(m) for m in K.ReduceMode] == ["replace", "dither", "meld"]
+    img = K.Image.new((2, 1), np.array([[1, 2, 3, 4, 5, 6, 7, 8]], np.uint8))
+    assert img.dimensions == (2, 1) and img.get_pixel(1, 0) == (5, 6, 7, 8)
+    assert img.into_raw_pixels().shape == (2, 4)
+    with pytest.raises(ValueError):
+        K.Image.new((3, 3), np.zeros(8, np.uint8))
+
+
+def test_shard_rules():
+    import kmeans_gpu_b200 as K
+
+    assert K.row_shards(8192, 8) == [(i * 1024, (i + 1) * 1024) for i in range(8)]
+    s = K.row_shards(513, 4)
+    assert s[0][0] == 0 and s[-1][1] == 513 and all(a[1] == b[0] for a, b in zip(s, s[1:]))
+    f = K.frame_shards(4096, 8)
+    assert [b - a for a, b in f] == [512] * 8
+    assert K.frame_shards(3, 4) == [(0, 0), (0, 1), (1, 2), (2, 3)]
+
+
+def test_synth_generator_is_stable(oracle):
+    """Known answers of the synthetic generator so CPU and GPU inputs agree."""
+    u = oracle.synth(4, seed=1)
+    b = oracle.synth(4, seed=2, blobs=512, first_pixel=5)
+    assert u[:, 3].tolist() == [255] * 4 and b[:, 3].tolist() == [255] * 4
+    # split generation == whole generation
+    whole = oracle.synth(1000, seed=3, blobs=32, frame=7)
+    parts = np.concatenate([oracle.synth(400, seed=3, blobs=32, frame=7), oracle.synth(600, first_pixel=400, seed=3, blobs=32, frame=7)])
+    assert np.array_equal(whole, parts)
