@@ -239,7 +239,7 @@ def run_ours(args):
                        "k": K_CLUSTERS, "bytes_per_px": BYTES_PER_PX, "l2": "work plane 1 GiB per GPU > 126 MB L2",
                        "exact_path_pixels_per_pass": stats["slow_pixels"] / max(stats["passes"], 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd_private<8,256,4>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd_private<KT=8,256 threads,4 px/thread>",
                          "kernel_ms": step_ms},
             "cpu_baseline": {"value": cpu_mpix, "unit": "Mpix/s", "cores": cpu_threads, "kind": "port",
                              "sample": "2048x2048 crop of the same synthetic image, 3 iterations, oracle/oracle.cpp "

@@ -120,7 +120,7 @@ void kmg_sort_palette_by_lightness(uint8_t* colors_rgba8, uint32_t count);
 
 /* ---- device-resident entry points (inputs already in HBM; used by batch callers, the bench and
  *      the stage-level parity tests).  Pointers are device pointers on ctx's device; `stream` is a
- *      cudaStream_t (NULL = the context's own stream).  Calls are asynchronous on `stream` unless
+ *      cudaStream_t (NULL = the CUDA default stream).  Calls are asynchronous on `stream` unless
  *      they return values to host memory, in which case they synchronise that stream. ---------- */
 
 typedef struct kmg_job kmg_job; /* one k-means problem resident on the device */

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,6 +27,14 @@
 #endif
 
 using namespace kmg;
+
+// Lloyd-pass variants (table length, threads, pixels/thread, saved-score certificate, min blocks/SM)
+#define LLOYD8 k_lloyd_private<8, 256, 4, true, 2>
+#define LLOYD8_B k_lloyd_private<8, 256, 2, true, 3>
+#define LLOYD8_C k_lloyd_private<8, 256, 2, true, 4>
+#define LLOYD8_D k_lloyd_private<8, 128, 4, true, 4>
+#define LLOYD16 k_lloyd_private<16, 256, 2, true, 2>
+#define LLOYD32 k_lloyd_private<32, 128, 4, false, 3>
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -147,7 +156,7 @@ struct kmg_ctx {
   int device = 0;
   int sms = 0;
   float* d_lut = nullptr;
-  cudaStream_t stream = nullptr;  // context stream for device-resident calls with stream == NULL
+  cudaStream_t stream = nullptr;  // context stream for set-up work (always synchronised before returning)
   std::mutex mu;
   std::vector<Workspace*> pool;
   std::atomic<uint64_t> launches{0};
@@ -299,18 +308,21 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   LAUNCHED(ctx);
   CHECK_LAUNCH();
   // opt in to > 48 KiB dynamic shared memory
-  CU(cudaFuncSetAttribute(k_lloyd_private<8, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
-  CU(cudaFuncSetAttribute(k_lloyd_private<16, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16));
-  CU(cudaFuncSetAttribute(k_lloyd_private<32, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 128 * 16));
+  CU(cudaFuncSetAttribute(LLOYD8, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+  CU(cudaFuncSetAttribute(LLOYD8_B, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+  CU(cudaFuncSetAttribute(LLOYD8_C, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+  CU(cudaFuncSetAttribute(LLOYD8_D, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 16));
+  CU(cudaFuncSetAttribute(LLOYD16, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16));
+  CU(cudaFuncSetAttribute(LLOYD32, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 128 * 16));
   const int big = MAX_K * (int)(sizeof(CentRec) + 4);
   CU(cudaFuncSetAttribute(k_lloyd_global<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_assign<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<0, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<1, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, k_lloyd_private<8, 256, 4>, 256, 8 * 256 * 16));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, k_lloyd_private<16, 256, 4>, 256, 16 * 256 * 16));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, k_lloyd_private<32, 128, 4>, 128, 32 * 128 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, LLOYD8, 256, 8 * 256 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, LLOYD16, 256, 16 * 256 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, LLOYD32, 128, 32 * 128 * 16));
   CU(cudaStreamSynchronize(ctx->stream));
   *out = ctx;
   return KMG_OK;
@@ -351,7 +363,9 @@ extern "C" void kmg_resized_dims(uint32_t w, uint32_t h, uint32_t max_size, uint
 // ------------------------------------------------------------------------------------------------
 // stage launchers (device pointers)
 
-static cudaStream_t pick_stream(kmg_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+// NULL is the CUDA (legacy) default stream, as everywhere in the runtime API — it orders with the
+// caller's default-stream work (torch's default stream is handle 0).
+static cudaStream_t pick_stream(kmg_ctx*, void* stream) { return (cudaStream_t)stream; }
 
 static int launch_convert(kmg_ctx* ctx, const uint8_t* d_rgba, uint64_t n, int cs, float* d_work, cudaStream_t s) {
   int grid = grid_for(ctx, n, 256, 8);
@@ -380,14 +394,23 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   const unsigned long long n = (unsigned long long)j->w * j->h;
   const int partial = (j->sharded && ctx->n_ranks > 1) ? 1 : 0;
   if (j->k <= 8) {
-    int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
-    k_lloyd_private<8, 256, 4><<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    static const int variant = getenv("KMG_LLOYD8_VARIANT") ? atoi(getenv("KMG_LLOYD8_VARIANT")) : 0;
+    if (variant == 1) {
+      LLOYD8_B<<<grid_for(ctx, n, 256 * 2, 3), 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    } else if (variant == 2) {
+      LLOYD8_C<<<grid_for(ctx, n, 256 * 2, 4), 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    } else if (variant == 3) {
+      LLOYD8_D<<<grid_for(ctx, n, 128 * 4, 4), 128, 8 * 128 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    } else {
+      int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
+      LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    }
   } else if (j->k <= 16) {
-    int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private16);
-    k_lloyd_private<16, 256, 4><<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    int grid = grid_for(ctx, n, 256 * 2, ctx->occ_private16);
+    LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
   } else if (j->k <= 32) {
     int grid = grid_for(ctx, n, 128 * 4, ctx->occ_private32);
-    k_lloyd_private<32, 128, 4><<<grid, 128, 32 * 128 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    LLOYD32<<<grid, 128, 32 * 128 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
   } else {
     size_t smem = (size_t)pad32(j->k) * sizeof(CentRec);
     int grid = grid_for(ctx, n, 256 * 4, smem > 96 * 1024 ? 1 : 2);

@@ -199,6 +199,144 @@ __device__ __forceinline__ void argmin_fast(const CentRec* __restrict__ tab, uns
   }
 }
 
+// Small tables (KT <= 16): all KT scores of a pixel stay in registers.  Min + index are tracked with
+// FSETP/FSEL/SEL; the certificate "no other score within eps of the best" is evaluated on the FMA
+// pipe instead of the (half-rate, otherwise saturated) ALU pipe:
+//   S = sum_j sat((s_j - m1) / eps)   is  >= KT - 1  iff every other score is >= eps away.
+template <int P, int KT>
+__device__ __forceinline__ void argmin_saved(const CentRec* __restrict__ tab, const Pix<P>& px, float lmax,
+                                             float cmax, float (&m1)[P], float (&eps)[P], unsigned int (&idx)[P],
+                                             bool (&certified)[P]) {
+  fast::PixCoef pc[P];
+  float s[KT][P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) pc[i] = fast::pix_coef(px.L[i], px.a[i], px.b[i], px.C[i]);
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    const float4 q0 = tab[j].q0;
+    const float2 q1 = *reinterpret_cast<const float2*>(&tab[j].q1);
+#pragma unroll
+    for (int i = 0; i < P; ++i) s[j][i] = fast::score(pc[i], q0, q1);
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    float m = s[0][i];
+    unsigned int ix = 0;
+#pragma unroll
+    for (int j = 1; j < KT; ++j) {
+      bool lt = s[j][i] < m;
+      m = lt ? s[j][i] : m;
+      ix = lt ? (unsigned int)j : ix;
+    }
+    m1[i] = m;
+    idx[i] = ix;
+    eps[i] = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
+    const float g = fast::rcp(eps[i]);
+    const float base = -m * g;
+    float S = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) S += __saturatef(fmaf(s[j][i], g, base));
+    certified[i] = S > (float)(KT - 1) - 1.0e-3f;
+  }
+}
+
+// Packed variant of argmin_saved for P even: pixels are processed two at a time with FFMA2/FADD2,
+// the table is read as duplicated pairs {q,q} (tab2: KT x 6 float2), the minimum is a 3-input-min
+// tournament and the winning index is recovered on the FMA pipe from the certificate terms:
+// with t_j = sat((s_j - m1)/eps) in {~0 (winner), 1 (everyone else)} for a certified pixel,
+//   R_m = sum_{j>=m} t_j (suffix sums),  S = R_0,  sum_j j*t_j = sum_{m>=1} R_m,
+// so idx = KT(KT-1)/2 - sum_{m>=1} R_m.  Uncertified pixels take the exact path, which recomputes
+// the index itself.
+template <int P, int KT>
+__device__ __forceinline__ void argmin_saved_x2(const float2* __restrict__ tab2, const Pix<P>& px, float lmax,
+                                                float cmax, float (&m1)[P], float (&eps)[P],
+                                                unsigned int (&idx)[P], bool (&certified)[P]) {
+  static_assert(P % 2 == 0, "pairs of pixels");
+  static_assert((KT & (KT - 1)) == 0, "table length must be a power of two");
+  constexpr int H = P / 2;
+  fast::f32x2 pp[H][5];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    fast::PixCoef c0 = fast::pix_coef(px.L[2 * h], px.a[2 * h], px.b[2 * h], px.C[2 * h]);
+    fast::PixCoef c1 = fast::pix_coef(px.L[2 * h + 1], px.a[2 * h + 1], px.b[2 * h + 1], px.C[2 * h + 1]);
+    pp[h][0] = fast::pack2(c0.p0, c1.p0);
+    pp[h][1] = fast::pack2(c0.p1, c1.p1);
+    pp[h][2] = fast::pack2(c0.p2, c1.p2);
+    pp[h][3] = fast::pack2(c0.p3, c1.p3);
+    pp[h][4] = fast::pack2(c0.p4, c1.p4);
+  }
+  fast::f32x2 s2[KT][H];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    const float4 qa = *reinterpret_cast<const float4*>(tab2 + j * 6);      // {Lc^2,Lc^2, Lc,Lc}
+    const float4 qb = *reinterpret_cast<const float4*>(tab2 + j * 6 + 2);  // {C2^2,C2^2, C2,C2}
+    const float4 qc = *reinterpret_cast<const float4*>(tab2 + j * 6 + 4);  // {ac,ac, bc,bc}
+    const fast::f32x2 q0x = fast::pack2(qa.x, qa.y), q0y = fast::pack2(qa.z, qa.w);
+    const fast::f32x2 q0z = fast::pack2(qb.x, qb.y), q0w = fast::pack2(qb.z, qb.w);
+    const fast::f32x2 q1x = fast::pack2(qc.x, qc.y), q1y = fast::pack2(qc.z, qc.w);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      fast::f32x2 s = fast::fma2(pp[h][0], q0y, q0x);
+      s = fast::fma2(pp[h][1], q0z, s);
+      s = fast::fma2(pp[h][2], q0w, s);
+      s = fast::fma2(pp[h][3], q1x, s);
+      s = fast::fma2(pp[h][4], q1y, s);
+      s2[j][h] = s;
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    float sa[KT], sb[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) fast::unpack2(s2[j][h], sa[j], sb[j]);
+    float ma = sa[0], mb = sb[0];
+#pragma unroll
+    for (int j = 1; j + 1 < KT; j += 2) {
+      ma = fast::min3(ma, sa[j], sa[j + 1]);
+      mb = fast::min3(mb, sb[j], sb[j + 1]);
+    }
+    if ((KT & 1) == 0) {
+      ma = fminf(ma, sa[KT - 1]);
+      mb = fminf(mb, sb[KT - 1]);
+    }
+    const float ea = fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax);
+    const float eb = fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax);
+    const float ga = fast::rcp(ea), gb = fast::rcp(eb);
+    const float ba = -ma * ga, bb = -mb * gb;
+    // t_j pairs, then a pairwise tree: at every level the sum of the odd-position entries is the
+    // count of indices with that bit set, so sum_j j*t_j = sum_b 2^b * B_b with depth log2(KT).
+    fast::f32x2 v[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+      v[j] = fast::pack2(__saturatef(fmaf(sa[j], ga, ba)), __saturatef(fmaf(sb[j], gb, bb)));
+    fast::f32x2 I = fast::pack2(0.0f, 0.0f);
+    float wgt = 1.0f;
+#pragma unroll
+    for (int n = KT; n > 1; n >>= 1) {
+      fast::f32x2 odd = v[1];
+#pragma unroll
+      for (int m = 1; m < n / 2; ++m) odd = fast::add2(odd, v[2 * m + 1]);
+      I = fast::fma2(odd, fast::pack2(wgt, wgt), I);
+      wgt *= 2.0f;
+#pragma unroll
+      for (int m = 0; m < n / 2; ++m) v[m] = fast::add2(v[2 * m], v[2 * m + 1]);
+    }
+    const fast::f32x2 R = v[0];
+    float Sa, Sb, Ia, Ib;
+    fast::unpack2(R, Sa, Sb);
+    fast::unpack2(I, Ia, Ib);
+    constexpr float TRI = (float)(KT * (KT - 1) / 2);
+    m1[2 * h] = ma;
+    m1[2 * h + 1] = mb;
+    eps[2 * h] = ea;
+    eps[2 * h + 1] = eb;
+    certified[2 * h] = Sa > (float)(KT - 1) - 1.0e-3f;
+    certified[2 * h + 1] = Sb > (float)(KT - 1) - 1.0e-3f;
+    idx[2 * h] = (unsigned int)__float2int_rn(TRI - Ia) & (unsigned int)(KT - 1);
+    idx[2 * h + 1] = (unsigned int)__float2int_rn(TRI - Ib) & (unsigned int)(KT - 1);
+  }
+}
+
 // Exact re-evaluation for one pixel (exact components + exact chroma).
 __device__ __noinline__ unsigned int argmin_exact(const CentRec* __restrict__ tab, unsigned int k, float L, float a,
                                                   float b, float C, float bound) {
@@ -423,27 +561,98 @@ __global__ void __launch_bounds__(256) k_finalize(JobPtrs J, int color_space) {
   finalize_pass<256>(J, color_space, false);
 }
 
-template <int KT, int THREADS, int P>
-__global__ void __launch_bounds__(THREADS) k_lloyd_private(JobPtrs J, const float4* __restrict__ work,
-                                                           unsigned long long n, int color_space,
-                                                           int distributed_partial) {
+template <int THREADS, int P, bool CHECK>
+__device__ __forceinline__ void lloyd_load(const float4* __restrict__ work, unsigned long long base,
+                                           unsigned long long n, float4 (&v)[P]) {
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    unsigned long long p = base + (unsigned long long)i * THREADS;
+    v[i] = (!CHECK || p < n) ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int KT, int THREADS, int P, bool SAVED, bool CHECK>
+__device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, const float2* __restrict__ s_tab2,
+                                           int4* __restrict__ s_acc,
+                                           const float4 (&v)[P], unsigned long long base, unsigned long long n,
+                                           unsigned int k, float lmax, float cmax, unsigned int tid,
+                                           unsigned int& slow) {
+  Pix<P> px;
+  bool valid[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    valid[i] = CHECK ? (base + (unsigned long long)i * THREADS) < n : true;
+    px.L[i] = v[i].x;
+    px.a[i] = v[i].y;
+    px.b[i] = v[i].z;
+    px.C[i] = v[i].w;
+  }
+  float m1[P], eps[P];
+  unsigned int idx[P];
+  bool certified[P];
+  if (SAVED) {
+    argmin_saved_x2<P, KT>(s_tab2, px, lmax, cmax, m1, eps, idx, certified);
+  } else {
+    float m2[P];
+    argmin_fast<P, KT>(s_tab, KT, px, m1, m2, idx);
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      eps[i] = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
+      certified[i] = m2[i] - m1[i] > eps[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    if (!certified[i] && valid[i]) {
+      idx[i] = argmin_exact(s_tab, k, px.L[i], px.a[i], px.b[i], px.C[i], m1[i] + eps[i]);
+      ++slow;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    if (valid[i]) {
+      int4* slot = s_acc + idx[i] * THREADS + tid;
+      int4 a = *slot;
+      a.x += ex::to_fixed(px.L[i]);
+      a.y += ex::to_fixed(px.a[i]);
+      a.z += ex::to_fixed(px.b[i]);
+      a.w += 1;
+      *slot = a;
+    }
+  }
+}
+
+template <int KT, int THREADS, int P, bool SAVED, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_lloyd_private(JobPtrs J, const float4* __restrict__ work,
+                                                                 unsigned long long n, int color_space,
+                                                                 int distributed_partial) {
   // KT: compile-time table length (k padded with MASKED entries), fully unrolled.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* s_acc = reinterpret_cast<int4*>(smem_raw);  // [KT][THREADS]
   __shared__ CentRec s_tab[KT];
+  __shared__ __align__(16) float2 s_tab2[KT * 6];  // the same table as duplicated pairs for FFMA2
   __shared__ bool s_last;
   JobState* st = J.st;
   if (st->done) return;
   const unsigned int tid = threadIdx.x;
   const unsigned int k = st->k;
-  for (unsigned int c = tid; c < KT; c += THREADS) s_tab[c] = J.tab[c];
+  for (unsigned int c = tid; c < KT; c += THREADS) {
+    CentRec r = J.tab[c];
+    s_tab[c] = r;
+    s_tab2[c * 6 + 0] = make_float2(r.q0.x, r.q0.x);
+    s_tab2[c * 6 + 1] = make_float2(r.q0.y, r.q0.y);
+    s_tab2[c * 6 + 2] = make_float2(r.q0.z, r.q0.z);
+    s_tab2[c * 6 + 3] = make_float2(r.q0.w, r.q0.w);
+    s_tab2[c * 6 + 4] = make_float2(r.q1.x, r.q1.x);
+    s_tab2[c * 6 + 5] = make_float2(r.q1.y, r.q1.y);
+  }
 #pragma unroll
   for (int c = 0; c < KT; ++c) s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
   const float lmax = st->lmax, cmax = st->cmax;
   __syncthreads();
 
   constexpr unsigned long long TILE = (unsigned long long)THREADS * P;
-  const unsigned long long tiles = (n + TILE - 1) / TILE;
+  const unsigned long long full_tiles = n / TILE;
   unsigned int since_flush = 0;
   unsigned int slow = 0;
 
@@ -466,46 +675,29 @@ __global__ void __launch_bounds__(THREADS) k_lloyd_private(JobPtrs J, const floa
     since_flush = 0;
   };
 
-  for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const unsigned long long base = tile * TILE + tid;
-    Pix<P> px;
-    bool valid[P];
+  // full tiles: no bounds checks in the hot loop; the next tile is in flight (registers) while the
+  // current one is processed, so HBM latency is hidden even at 2 blocks per SM.
+  {
+    float4 cur[P], nxt[P];
+    unsigned long long tile = blockIdx.x;
+    if (tile < full_tiles) lloyd_load<THREADS, P, false>(work, tile * TILE + tid, n, cur);
+    for (; tile < full_tiles; tile += gridDim.x) {
+      const unsigned long long next = tile + gridDim.x;
+      if (next < full_tiles) lloyd_load<THREADS, P, false>(work, next * TILE + tid, n, nxt);
+      lloyd_tile<KT, THREADS, P, SAVED, false>(s_tab, s_tab2, s_acc, cur, tile * TILE + tid, n, k, lmax, cmax, tid, slow);
+      since_flush += P;
+      // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
+      if (since_flush + P > 240) flush();
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      unsigned long long p = base + (unsigned long long)i * THREADS;
-      valid[i] = p < n;
-      float4 v = valid[i] ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-      px.L[i] = v.x;
-      px.a[i] = v.y;
-      px.b[i] = v.z;
-      px.C[i] = v.w;
+      for (int i = 0; i < P; ++i) cur[i] = nxt[i];
     }
-    float m1[P], m2[P];
-    unsigned int idx[P];
-    argmin_fast<P, KT>(s_tab, KT, px, m1, m2, idx);
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      float eps = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
-      if (m2[i] - m1[i] <= eps && valid[i]) {
-        idx[i] = argmin_exact(s_tab, k, px.L[i], px.a[i], px.b[i], px.C[i], m1[i] + eps);
-        ++slow;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      if (valid[i]) {
-        int4* slot = s_acc + idx[i] * THREADS + tid;
-        int4 a = *slot;
-        a.x += ex::to_fixed(px.L[i]);
-        a.y += ex::to_fixed(px.a[i]);
-        a.z += ex::to_fixed(px.b[i]);
-        a.w += 1;
-        *slot = a;
-      }
-    }
-    since_flush += P;
-    // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
+  }
+  // ragged tail (< TILE pixels), taken by the block whose turn it would be
+  if (full_tiles * TILE < n && blockIdx.x == (unsigned int)(full_tiles % gridDim.x)) {
     if (since_flush + P > 240) flush();
+    float4 tail[P];
+    lloyd_load<THREADS, P, true>(work, full_tiles * TILE + tid, n, tail);
+    lloyd_tile<KT, THREADS, P, SAVED, true>(s_tab, s_tab2, s_acc, tail, full_tiles * TILE + tid, n, k, lmax, cmax, tid, slow);
   }
   flush();
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);

@@ -127,6 +127,39 @@ __device__ __forceinline__ int to_fixed(float v) { return __float2int_rn(fmul(v,
 
 namespace fast {
 
+// MUFU.RCP, 1 ulp, one instruction (the IEEE __frcp_rn costs ~12 with a slow-path call).
+__device__ __forceinline__ float rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Blackwell packed-f32x2 arithmetic (SASS FFMA2 / FADD2): one issue slot, two lanes of work.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // Per-pixel coefficients of the reduced CIE94 score (see DESIGN.md "assignment"):
 //   d^2(p,c) = [L^2 + C1^2/SC^2] + Lc^2 + p0*Lc + p1*C2^2 + p2*C2 + p3*ac + p4*bc
 // with p0 = -2L, p1 = 1/SC^2, p2 = 2*C1*(1/SH^2 - 1/SC^2), p3 = -2a/SH^2, p4 = -2b/SH^2,
@@ -137,8 +170,8 @@ struct PixCoef {
 __device__ __forceinline__ PixCoef pix_coef(float L, float a, float b, float C1) {
   float SC = fmaf(0.045f, C1, 1.0f);
   float SH = fmaf(0.015f, C1, 1.0f);
-  float rSC = __frcp_rn(SC);
-  float rSH = __frcp_rn(SH);
+  float rSC = rcp(SC);
+  float rSH = rcp(SH);
   PixCoef p;
   p.p1 = rSC * rSC;
   float hs = rSH * rSH;
@@ -172,7 +205,7 @@ __device__ __forceinline__ float lab_f(float t) {
   float lg = __log2f(t);
   float y0 = exp2f(lg * 0.33333334f);
   // one Newton step for the cube root, then the (1/3)_f32 vs 1/3 exponent correction
-  float r = __frcp_rn(y0 * y0);
+  float r = rcp(y0 * y0);
   float y1 = fmaf(y0, 0.6666667f, 0.33333334f * t * r);
   y1 = y1 * fmaf(6.8862e-9f, lg, 1.0f);  // t^(0.3333333432674408 - 1/3) = 2^(9.934e-9 * log2 t)
   float lin = fmaf(7.787f, t, 16.0f / 116.0f);
