@@ -28,13 +28,13 @@
 
 using namespace kmg;
 
-// Lloyd-pass variants (table length, threads, pixels/thread, saved-score certificate, min blocks/SM)
-#define LLOYD8 k_lloyd_private<8, 256, 4, true, 2>
-#define LLOYD8_B k_lloyd_private<8, 256, 2, true, 3>
-#define LLOYD8_C k_lloyd_private<8, 256, 2, true, 4>
-#define LLOYD8_D k_lloyd_private<8, 128, 4, true, 4>
-#define LLOYD16 k_lloyd_private<16, 256, 2, true, 2>
-#define LLOYD32 k_lloyd_private<32, 128, 4, false, 3>
+// Lloyd-pass variants: <table length (0 = runtime), accumulator capacity, threads, pixels/thread,
+// thread-private accumulators, min blocks/SM>
+#define LLOYD8 k_lloyd<8, 8, 256, 4, true, 2>
+#define LLOYD16 k_lloyd<16, 16, 256, 2, true, 2>
+#define LLOYD32 k_lloyd<0, 32, 128, 4, true, 3>
+#define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
+static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -187,9 +187,17 @@ struct kmg_job {
   float* d_xfer = nullptr;  // 4 floats, colour broadcast during distributed init
 };
 
+// Accumulator copies: the thread-private kernels (k <= 32) flush rarely, 8 copies are plenty; the
+// global-reduction kernel adds 4 values per pixel, so every resident block gets its own copy
+// (bounded to 8 MiB) and same-address serialisation in L2 disappears.
+static uint32_t job_acc_copies(uint32_t k) {
+  if (k <= 32) return 8;
+  size_t cap = ((size_t)8 << 20) / ((size_t)k * 32);
+  return (uint32_t)std::max<size_t>(8, std::min<size_t>(304, cap));
+}
 static size_t job_blob_bytes(uint32_t k) {
   size_t kp = pad32(k);
-  return 256 + (size_t)k * 16 + kp * sizeof(CentRec) + (size_t)(ACC_COPIES + 1) * k * 4 * 8 + (size_t)k * 8 + (size_t)k * 4 + 64;
+  return 256 + (size_t)k * 16 + kp * sizeof(CentRec) + (size_t)(job_acc_copies(k) + 1) * k * 4 * 8 + (size_t)k * 8 + (size_t)k * 4 + 64;
 }
 static void job_carve(kmg_job* j, void* blob) {
   unsigned char* b = (unsigned char*)blob;
@@ -201,7 +209,8 @@ static void job_carve(kmg_job* j, void* blob) {
   j->P.tab = (CentRec*)b;
   b += kp * sizeof(CentRec);
   j->P.acc = (long long*)b;
-  b += (size_t)ACC_COPIES * j->k * 4 * 8;
+  j->P.acc_copies = job_acc_copies(j->k);
+  b += (size_t)j->P.acc_copies * j->k * 4 * 8;
   j->P.last = (long long*)b;
   b += (size_t)j->k * 4 * 8;
   j->P.keys = (unsigned long long*)b;
@@ -308,21 +317,18 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   LAUNCHED(ctx);
   CHECK_LAUNCH();
   // opt in to > 48 KiB dynamic shared memory
+  const int big = (int)(tab_smem_bytes(MAX_K) + MAX_K * 4);
   CU(cudaFuncSetAttribute(LLOYD8, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD8_B, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD8_C, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD8_D, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 16));
   CU(cudaFuncSetAttribute(LLOYD16, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD32, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 128 * 16));
-  const int big = MAX_K * (int)(sizeof(CentRec) + 4);
-  CU(cudaFuncSetAttribute(k_lloyd_global<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU(cudaFuncSetAttribute(LLOYD32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LLOYD32_SMEM));
+  CU(cudaFuncSetAttribute(LLOYDG, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_assign<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<0, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<1, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, LLOYD8, 256, 8 * 256 * 16));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, LLOYD16, 256, 16 * 256 * 16));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, LLOYD32, 128, 32 * 128 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, LLOYD32, 128, LLOYD32_SMEM));
   CU(cudaStreamSynchronize(ctx->stream));
   *out = ctx;
   return KMG_OK;
@@ -394,27 +400,18 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   const unsigned long long n = (unsigned long long)j->w * j->h;
   const int partial = (j->sharded && ctx->n_ranks > 1) ? 1 : 0;
   if (j->k <= 8) {
-    static const int variant = getenv("KMG_LLOYD8_VARIANT") ? atoi(getenv("KMG_LLOYD8_VARIANT")) : 0;
-    if (variant == 1) {
-      LLOYD8_B<<<grid_for(ctx, n, 256 * 2, 3), 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
-    } else if (variant == 2) {
-      LLOYD8_C<<<grid_for(ctx, n, 256 * 2, 4), 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
-    } else if (variant == 3) {
-      LLOYD8_D<<<grid_for(ctx, n, 128 * 4, 4), 128, 8 * 128 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
-    } else {
-      int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
-      LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
-    }
+    int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
+    LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
   } else if (j->k <= 16) {
     int grid = grid_for(ctx, n, 256 * 2, ctx->occ_private16);
     LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
   } else if (j->k <= 32) {
     int grid = grid_for(ctx, n, 128 * 4, ctx->occ_private32);
-    LLOYD32<<<grid, 128, 32 * 128 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    LLOYD32<<<grid, 128, LLOYD32_SMEM, s>>>(j->P, j->work, n, j->color_space, partial);
   } else {
-    size_t smem = (size_t)pad32(j->k) * sizeof(CentRec);
-    int grid = grid_for(ctx, n, 256 * 4, smem > 96 * 1024 ? 1 : 2);
-    k_lloyd_global<256, 4><<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial);
+    size_t smem = tab_smem_bytes(pad32(j->k));
+    int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
+    LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial);
   }
   LAUNCHED(ctx);
   CHECK_LAUNCH();
@@ -438,16 +435,13 @@ static int launch_remap_mode(kmg_job* j, const uint8_t* d_rgba, uint32_t w, unsi
   uint32_t* out = (uint32_t*)d_out;
   if (j->k <= 8) {
     int grid = grid_for(ctx, groups, 256, 4);
-    k_remap<MODE, 8, 256><<<grid, 256, 8 * 36, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+    k_remap<MODE, 8, 256><<<grid, 256, tab_smem_bytes(8) + 8 * 4, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
   } else if (j->k <= 16) {
     int grid = grid_for(ctx, groups, 256, 4);
-    k_remap<MODE, 16, 256><<<grid, 256, 16 * 36, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
-  } else if (j->k <= 32) {
-    int grid = grid_for(ctx, groups, 256, 4);
-    k_remap<MODE, 32, 256><<<grid, 256, 32 * 36, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+    k_remap<MODE, 16, 256><<<grid, 256, tab_smem_bytes(16) + 16 * 4, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
   } else {
-    size_t smem = (size_t)pad32(j->k) * 36;
-    int grid = grid_for(ctx, groups, 256, smem > 96 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
+    size_t smem = tab_smem_bytes(pad32(j->k)) + (size_t)pad32(j->k) * 4;
+    int grid = grid_for(ctx, groups, 256, smem > 100 * 1024 ? 1 : (smem > 60 * 1024 ? 2 : 3));
     k_remap<MODE, 0, 256><<<grid, 256, smem, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
   }
   LAUNCHED(ctx);
@@ -775,8 +769,8 @@ extern "C" int kmg_dev_assign(kmg_ctx* ctx, const float* d_work, uint64_t n, con
   TempJob t;
   TRY(t.setup(ctx, (uint32_t)n, 1, cent, k, KMG_LAB, s));
   TRY(launch_prepare(&t.job, false, s));
-  size_t smem = (size_t)pad32(k) * sizeof(CentRec);
-  int grid = grid_for(ctx, n, 256 * 4, smem > 96 * 1024 ? 1 : 2);
+  size_t smem = tab_smem_bytes(pad32(k));
+  int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
   k_assign<256, 4><<<grid, 256, smem, s>>>(t.job.P, (const float4*)d_work, n, d_labels);
   LAUNCHED(ctx);
   CHECK_LAUNCH();

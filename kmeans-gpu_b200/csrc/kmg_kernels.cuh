@@ -18,15 +18,16 @@
 
 namespace kmg {
 
-// One centroid as the kernels see it.  q0 = {Lc^2, Lc, C2^2, C2}, q1 = {ac, bc, 0, 0}.
-// Duplicates of a lower-index centroid and padding entries carry q0.x = MASKED so they can
-// never win (the reference's strict '<' scan keeps the lowest index on exact ties anyway).
-struct __align__(16) CentRec {
-  float4 q0;
-  float4 q1;
+// One centroid as the kernels see it: the six constants of the reduced score,
+//   q = {Lc^2, Lc, C2^2, C2, ac, bc}   (24 bytes, records are dense: 8 of them = twelve float4).
+// Packed FFMA2 takes them as scalar-broadcast operands, so nothing is duplicated.  Duplicates of
+// a lower-index centroid and padding entries carry q[0] = MASKED so they can never win (the
+// reference's strict '<' scan keeps the lowest index on exact ties anyway).
+struct __align__(8) CentRec {
+  float q[6];
 };
 constexpr float MASKED = 1.0e30f;
-constexpr int MAX_K = 4096;  // table = 128 KiB of shared memory at most
+constexpr int MAX_K = 4096;  // table = 104 KiB of shared memory at most
 
 struct JobState {
   unsigned int ticket;   // blocks finished in the current pass
@@ -48,14 +49,28 @@ struct JobPtrs {
   JobState* st;
   float4* cent;                // k
   CentRec* tab;                // k padded to a multiple of 32 with MASKED entries
-  long long* acc;              // ACC_COPIES x k x 4  (sum0,sum1,sum2,count), fixed-point 2^-16
+  long long* acc;              // acc_copies x k x 4  (sum0,sum1,sum2,count), fixed-point 2^-16
   long long* last;             // k x 4 — the reduced sums of the last finalised pass
   unsigned long long* keys;    // k  — arg-max keys of the init rounds
   uint32_t* pal;               // k  — centroids reverted to RGBA8
+  unsigned int acc_copies;     // privatised accumulator copies (block b adds into copy b % acc_copies)
 };
-constexpr int ACC_COPIES = 8;
 
 __host__ __device__ inline unsigned int pad32(unsigned int k) { return (k + 31u) & ~31u; }
+
+// Shared-memory copy of the table: every chunk of 8 records (192 B) is followed by 16 B of padding,
+// so chunk bases advance by an odd number of 16-byte bank groups and lanes that read *different*
+// chunks (winning-chunk rescan, cooperative exact path) do not all collide on the same banks.
+constexpr unsigned int CHUNK_BYTES = 8 * 24 + 16;
+__host__ __device__ inline size_t tab_smem_bytes(unsigned int kp) { return (size_t)(kp / 8) * CHUNK_BYTES; }
+__device__ __forceinline__ const CentRec* rec_at(const CentRec* tab, unsigned int j) {
+  return reinterpret_cast<const CentRec*>(reinterpret_cast<const unsigned char*>(tab) + (size_t)(j >> 3) * CHUNK_BYTES +
+                                          (j & 7u) * 24u);
+}
+__device__ __forceinline__ void tab_to_smem(CentRec* s_tab, const CentRec* __restrict__ g_tab, unsigned int kp,
+                                            unsigned int tid, unsigned int nthreads) {
+  for (unsigned int c = tid; c < kp; c += nthreads) *const_cast<CentRec*>(rec_at(s_tab, c)) = g_tab[c];
+}
 
 // ------------------------------------------------------------------------------------------------
 // Small utilities
@@ -102,15 +117,19 @@ __device__ void build_table(const JobPtrs& J, unsigned int k, int color_space, b
         float4 u = J.cent[i];
         dup |= (u.x == v.x && u.y == v.y && u.z == v.z);
       }
-      r.q0 = make_float4(dup ? MASKED : v.x * v.x, v.x, c2 * c2, c2);
-      r.q1 = make_float4(v.y, v.z, 0.0f, 0.0f);
+      r.q[0] = dup ? MASKED : v.x * v.x;
+      r.q[1] = v.x;
+      r.q[2] = c2 * c2;
+      r.q[3] = c2;
+      r.q[4] = v.y;
+      r.q[5] = v.z;
       lmax = fmaxf(lmax, fabsf(v.x));
       cmax = fmaxf(cmax, c2);
       if (want_palette)
         J.pal[c] = color_space == 0 ? ex::lab_to_rgba8(v.x, v.y, v.z) : ex::rgbf_to_rgba8(v.x, v.y, v.z, v.w);
     } else {
-      r.q0 = make_float4(MASKED, 0.0f, 0.0f, 0.0f);
-      r.q1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      r.q[0] = MASKED;
+      r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
     }
     J.tab[c] = r;
   }
@@ -160,128 +179,131 @@ __global__ void __launch_bounds__(256) k_prepare(JobPtrs J, int color_space, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Certified nearest-centroid search over a shared-memory table, P pixels per thread.
+// Certified nearest-centroid search over a shared-memory table.
 //
-// Fast pass: 5 FMA per (pixel, centroid) + min / second-min tracking.  A pixel is certified when
-// second - best > eps (eps bounds every rounding difference between the fast score and the
-// reference's f32 distance, plus extra_eps supplied by callers whose pixel is itself approximate).
-// Otherwise every centroid whose fast score is within eps of the best is re-evaluated with the
-// exact reference arithmetic, scanning in index order with strict '<' from 100000.0
-// (find_centroid.wgsl:29-41), which is exactly what the reference does over those candidates.
+// Fast pass: the reduced CIE94 score (5 FMA per pixel x centroid, see kmg_math.cuh) evaluated for
+// two pixels at a time with Blackwell's packed FFMA2, the table holding every value as a
+// duplicated pair.  A pixel is *certified* when no other centroid's score lies within eps of the
+// best one, eps bounding every rounding difference between the fast score and the reference's f32
+// distance (plus, in the remap kernels, the error of the approximate Lab).  The certificate
+// "S = sum_j sat((s_j - m1)/eps) >= K - 1" runs on the FMA pipe, and the same terms give the index:
+// sum_j j*t_j = sum_b 2^b * (sum of t_j over j with bit b set), evaluated as a pairwise tree.
+// Uncertified pixels are re-evaluated with exact reference arithmetic (warp_exact_argmin), so
+// labels are the reference's bit for bit, not "up to near ties".
+
 template <int P>
 struct Pix {
   float L[P], a[P], b[P], C[P];
 };
 
-template <int P, int UNROLL>
-__device__ __forceinline__ void argmin_fast(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
-                                            float (&m1)[P], float (&m2)[P], unsigned int (&idx)[P]) {
-  fast::PixCoef pc[P];
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    pc[i] = fast::pix_coef(px.L[i], px.a[i], px.b[i], px.C[i]);
-    m1[i] = 3.0e38f;
-    m2[i] = 3.0e38f;
-    idx[i] = 0;
-  }
-#pragma unroll UNROLL
-  for (unsigned int j = 0; j < kp; ++j) {
-    const float4 q0 = tab[j].q0;
-    const float2 q1 = *reinterpret_cast<const float2*>(&tab[j].q1);
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      float s = fast::score(pc[i], q0, q1);
-      m2[i] = fminf(m2[i], fmaxf(s, m1[i]));
-      bool lt = s < m1[i];
-      m1[i] = lt ? s : m1[i];
-      idx[i] = lt ? j : idx[i];
-    }
-  }
+__device__ __forceinline__ float tournament8(const float (&s)[8]) {
+  float m = fast::min3(s[0], s[1], s[2]);
+  m = fast::min3(m, s[3], s[4]);
+  m = fast::min3(m, s[5], s[6]);
+  return fminf(m, s[7]);
 }
 
-// Small tables (KT <= 16): all KT scores of a pixel stay in registers.  Min + index are tracked with
-// FSETP/FSEL/SEL; the certificate "no other score within eps of the best" is evaluated on the FMA
-// pipe instead of the (half-rate, otherwise saturated) ALU pipe:
-//   S = sum_j sat((s_j - m1) / eps)   is  >= KT - 1  iff every other score is >= eps away.
-template <int P, int KT>
-__device__ __forceinline__ void argmin_saved(const CentRec* __restrict__ tab, const Pix<P>& px, float lmax,
-                                             float cmax, float (&m1)[P], float (&eps)[P], unsigned int (&idx)[P],
-                                             bool (&certified)[P]) {
-  fast::PixCoef pc[P];
-  float s[KT][P];
-#pragma unroll
-  for (int i = 0; i < P; ++i) pc[i] = fast::pix_coef(px.L[i], px.a[i], px.b[i], px.C[i]);
-#pragma unroll
-  for (int j = 0; j < KT; ++j) {
-    const float4 q0 = tab[j].q0;
-    const float2 q1 = *reinterpret_cast<const float2*>(&tab[j].q1);
-#pragma unroll
-    for (int i = 0; i < P; ++i) s[j][i] = fast::score(pc[i], q0, q1);
-  }
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    float m = s[0][i];
-    unsigned int ix = 0;
-#pragma unroll
-    for (int j = 1; j < KT; ++j) {
-      bool lt = s[j][i] < m;
-      m = lt ? s[j][i] : m;
-      ix = lt ? (unsigned int)j : ix;
-    }
-    m1[i] = m;
-    idx[i] = ix;
-    eps[i] = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
-    const float g = fast::rcp(eps[i]);
-    const float base = -m * g;
-    float S = 0.0f;
-#pragma unroll
-    for (int j = 0; j < KT; ++j) S += __saturatef(fmaf(s[j][i], g, base));
-    certified[i] = S > (float)(KT - 1) - 1.0e-3f;
-  }
-}
-
-// Packed variant of argmin_saved for P even: pixels are processed two at a time with FFMA2/FADD2,
-// the table is read as duplicated pairs {q,q} (tab2: KT x 6 float2), the minimum is a 3-input-min
-// tournament and the winning index is recovered on the FMA pipe from the certificate terms:
-// with t_j = sat((s_j - m1)/eps) in {~0 (winner), 1 (everyone else)} for a certified pixel,
-//   R_m = sum_{j>=m} t_j (suffix sums),  S = R_0,  sum_j j*t_j = sum_{m>=1} R_m,
-// so idx = KT(KT-1)/2 - sum_{m>=1} R_m.  Uncertified pixels take the exact path, which recomputes
-// the index itself.
-template <int P, int KT>
-__device__ __forceinline__ void argmin_saved_x2(const float2* __restrict__ tab2, const Pix<P>& px, float lmax,
-                                                float cmax, float (&m1)[P], float (&eps)[P],
-                                                unsigned int (&idx)[P], bool (&certified)[P]) {
-  static_assert(P % 2 == 0, "pairs of pixels");
+// Certificate + index over KT saved scores of one pixel pair (sa: first pixel, sb: second).
+template <int KT>
+__device__ __forceinline__ void certify_pair(const float (&sa)[KT], const float (&sb)[KT], float ma, float mb,
+                                             float ea, float eb, bool& ca, bool& cb, unsigned int& ia,
+                                             unsigned int& ib) {
   static_assert((KT & (KT - 1)) == 0, "table length must be a power of two");
+  const float ga = fast::rcp(ea), gb = fast::rcp(eb);
+  const float ba = -ma * ga, bb = -mb * gb;
+  fast::f32x2 v[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+    v[j] = fast::pack2(__saturatef(fmaf(sa[j], ga, ba)), __saturatef(fmaf(sb[j], gb, bb)));
+  fast::f32x2 I = fast::pack2(0.0f, 0.0f);
+  float wgt = 1.0f;
+#pragma unroll
+  for (int n = KT; n > 1; n >>= 1) {
+    fast::f32x2 odd = v[1];
+#pragma unroll
+    for (int m = 1; m < n / 2; ++m) odd = fast::add2(odd, v[2 * m + 1]);
+    I = fast::fma2(odd, fast::pack2(wgt, wgt), I);
+    wgt *= 2.0f;
+#pragma unroll
+    for (int m = 0; m < n / 2; ++m) v[m] = fast::add2(v[2 * m], v[2 * m + 1]);
+  }
+  float Sa, Sb, Ia, Ib;
+  fast::unpack2(v[0], Sa, Sb);
+  fast::unpack2(I, Ia, Ib);
+  constexpr float TRI = (float)(KT * (KT - 1) / 2);
+  ca = Sa > (float)(KT - 1) - 1.0e-3f;
+  cb = Sb > (float)(KT - 1) - 1.0e-3f;
+  ia = (unsigned int)__float2int_rn(TRI - Ia) & (unsigned int)(KT - 1);
+  ib = (unsigned int)__float2int_rn(TRI - Ib) & (unsigned int)(KT - 1);
+}
+
+__device__ __forceinline__ void pack_coefs(const fast::PixCoef& c0, const fast::PixCoef& c1, fast::f32x2 (&pp)[5]) {
+  pp[0] = fast::pack2(c0.p0, c1.p0);
+  pp[1] = fast::pack2(c0.p1, c1.p1);
+  pp[2] = fast::pack2(c0.p2, c1.p2);
+  pp[3] = fast::pack2(c0.p3, c1.p3);
+  pp[4] = fast::pack2(c0.p4, c1.p4);
+}
+__device__ __forceinline__ fast::f32x2 score2(const fast::f32x2 (&pp)[5], const float* q) {
+  fast::f32x2 s = fast::fma2(pp[0], fast::pack2(q[1], q[1]), fast::pack2(q[0], q[0]));
+  s = fast::fma2(pp[1], fast::pack2(q[2], q[2]), s);
+  s = fast::fma2(pp[2], fast::pack2(q[3], q[3]), s);
+  s = fast::fma2(pp[3], fast::pack2(q[4], q[4]), s);
+  s = fast::fma2(pp[4], fast::pack2(q[5], q[5]), s);
+  return s;
+}
+__device__ __forceinline__ float score1(const fast::PixCoef& p, const float* q) {
+  float s = fmaf(p.p0, q[1], q[0]);
+  s = fmaf(p.p1, q[2], s);
+  s = fmaf(p.p2, q[3], s);
+  s = fmaf(p.p3, q[4], s);
+  s = fmaf(p.p4, q[5], s);
+  return s;
+}
+// One chunk of 8 records = twelve 128-bit shared-memory loads into registers.
+__device__ __forceinline__ void load_chunk(const CentRec* chunk, float (&f)[48]) {
+  const float4* c4 = reinterpret_cast<const float4*>(chunk);
+#pragma unroll
+  for (int u = 0; u < 12; ++u) {
+    const float4 t = c4[u];
+    f[4 * u + 0] = t.x;
+    f[4 * u + 1] = t.y;
+    f[4 * u + 2] = t.z;
+    f[4 * u + 3] = t.w;
+  }
+}
+
+// Error bound of a score gap.  CONV (remap kernels): the pixel itself is approximate (fast Lab),
+// so the gap may additionally move by |grad d^2| * LAB_ERR summed over the two candidates:
+// |grad d^2| <= 2.5 * D_E, D_E <= SC * d  =>  econv * sqrt(d^2) with econv = 5 * LAB_ERR * SC and
+// d^2 = best score + the pixel-only part of the squared distance (pconst).
+template <bool CONV>
+__device__ __forceinline__ float total_eps(float eps0, float m, float econv, float pconst) {
+  if (!CONV) return eps0;
+  return eps0 + econv * sqrtf(fmaxf(m + pconst, 0.0f) + eps0) + 3.0e-6f;
+}
+
+// Small tables (KT = 8 or 16, compile time): all KT scores of a pixel stay in registers.
+template <int P, int KT, bool CONV>
+__device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, const Pix<P>& px, float lmax,
+                                             float cmax, const float (&econv)[P], const float (&pconst)[P],
+                                             float (&eps)[P], unsigned int (&idx)[P], bool (&certified)[P]) {
+  static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::f32x2 pp[H][5];
 #pragma unroll
-  for (int h = 0; h < H; ++h) {
-    fast::PixCoef c0 = fast::pix_coef(px.L[2 * h], px.a[2 * h], px.b[2 * h], px.C[2 * h]);
-    fast::PixCoef c1 = fast::pix_coef(px.L[2 * h + 1], px.a[2 * h + 1], px.b[2 * h + 1], px.C[2 * h + 1]);
-    pp[h][0] = fast::pack2(c0.p0, c1.p0);
-    pp[h][1] = fast::pack2(c0.p1, c1.p1);
-    pp[h][2] = fast::pack2(c0.p2, c1.p2);
-    pp[h][3] = fast::pack2(c0.p3, c1.p3);
-    pp[h][4] = fast::pack2(c0.p4, c1.p4);
-  }
+  for (int h = 0; h < H; ++h)
+    pack_coefs(fast::pix_coef(px.L[2 * h], px.a[2 * h], px.b[2 * h], px.C[2 * h]),
+               fast::pix_coef(px.L[2 * h + 1], px.a[2 * h + 1], px.b[2 * h + 1], px.C[2 * h + 1]), pp[h]);
   fast::f32x2 s2[KT][H];
 #pragma unroll
-  for (int j = 0; j < KT; ++j) {
-    const float4 qa = *reinterpret_cast<const float4*>(tab2 + j * 6);      // {Lc^2,Lc^2, Lc,Lc}
-    const float4 qb = *reinterpret_cast<const float4*>(tab2 + j * 6 + 2);  // {C2^2,C2^2, C2,C2}
-    const float4 qc = *reinterpret_cast<const float4*>(tab2 + j * 6 + 4);  // {ac,ac, bc,bc}
-    const fast::f32x2 q0x = fast::pack2(qa.x, qa.y), q0y = fast::pack2(qa.z, qa.w);
-    const fast::f32x2 q0z = fast::pack2(qb.x, qb.y), q0w = fast::pack2(qb.z, qb.w);
-    const fast::f32x2 q1x = fast::pack2(qc.x, qc.y), q1y = fast::pack2(qc.z, qc.w);
+  for (int c = 0; c < KT; c += 8) {
+    float f[48];
+    load_chunk(rec_at(tab, c), f);
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      fast::f32x2 s = fast::fma2(pp[h][0], q0y, q0x);
-      s = fast::fma2(pp[h][1], q0z, s);
-      s = fast::fma2(pp[h][2], q0w, s);
-      s = fast::fma2(pp[h][3], q1x, s);
-      s = fast::fma2(pp[h][4], q1y, s);
-      s2[j][h] = s;
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) s2[c + j][h] = score2(pp[h], f + 6 * j);
     }
   }
 #pragma unroll
@@ -295,67 +317,148 @@ __device__ __forceinline__ void argmin_saved_x2(const float2* __restrict__ tab2,
       ma = fast::min3(ma, sa[j], sa[j + 1]);
       mb = fast::min3(mb, sb[j], sb[j + 1]);
     }
-    if ((KT & 1) == 0) {
-      ma = fminf(ma, sa[KT - 1]);
-      mb = fminf(mb, sb[KT - 1]);
-    }
-    const float ea = fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax);
-    const float eb = fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax);
-    const float ga = fast::rcp(ea), gb = fast::rcp(eb);
-    const float ba = -ma * ga, bb = -mb * gb;
-    // t_j pairs, then a pairwise tree: at every level the sum of the odd-position entries is the
-    // count of indices with that bit set, so sum_j j*t_j = sum_b 2^b * B_b with depth log2(KT).
-    fast::f32x2 v[KT];
-#pragma unroll
-    for (int j = 0; j < KT; ++j)
-      v[j] = fast::pack2(__saturatef(fmaf(sa[j], ga, ba)), __saturatef(fmaf(sb[j], gb, bb)));
-    fast::f32x2 I = fast::pack2(0.0f, 0.0f);
-    float wgt = 1.0f;
-#pragma unroll
-    for (int n = KT; n > 1; n >>= 1) {
-      fast::f32x2 odd = v[1];
-#pragma unroll
-      for (int m = 1; m < n / 2; ++m) odd = fast::add2(odd, v[2 * m + 1]);
-      I = fast::fma2(odd, fast::pack2(wgt, wgt), I);
-      wgt *= 2.0f;
-#pragma unroll
-      for (int m = 0; m < n / 2; ++m) v[m] = fast::add2(v[2 * m], v[2 * m + 1]);
-    }
-    const fast::f32x2 R = v[0];
-    float Sa, Sb, Ia, Ib;
-    fast::unpack2(R, Sa, Sb);
-    fast::unpack2(I, Ia, Ib);
-    constexpr float TRI = (float)(KT * (KT - 1) / 2);
-    m1[2 * h] = ma;
-    m1[2 * h + 1] = mb;
-    eps[2 * h] = ea;
-    eps[2 * h + 1] = eb;
-    certified[2 * h] = Sa > (float)(KT - 1) - 1.0e-3f;
-    certified[2 * h + 1] = Sb > (float)(KT - 1) - 1.0e-3f;
-    idx[2 * h] = (unsigned int)__float2int_rn(TRI - Ia) & (unsigned int)(KT - 1);
-    idx[2 * h + 1] = (unsigned int)__float2int_rn(TRI - Ib) & (unsigned int)(KT - 1);
+    ma = fminf(ma, sa[KT - 1]);
+    mb = fminf(mb, sb[KT - 1]);
+    eps[2 * h] = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, econv[2 * h], pconst[2 * h]);
+    eps[2 * h + 1] = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, econv[2 * h + 1],
+                                     pconst[2 * h + 1]);
+    certify_pair<KT>(sa, sb, ma, mb, eps[2 * h], eps[2 * h + 1], certified[2 * h], certified[2 * h + 1], idx[2 * h],
+                     idx[2 * h + 1]);
   }
 }
 
-// Exact re-evaluation for one pixel (exact components + exact chroma).
-__device__ __noinline__ unsigned int argmin_exact(const CentRec* __restrict__ tab, unsigned int k, float L, float a,
-                                                  float b, float C, float bound) {
-  fast::PixCoef pc = fast::pix_coef(L, a, b, C);
-  float best = 100000.0f;
-  unsigned int found = 0;
-  for (unsigned int j = 0; j < k; ++j) {
-    const float4 q0 = tab[j].q0;
-    const float4 q1 = tab[j].q1;
-    float s = fast::score(pc, q0, make_float2(q1.x, q1.y));
-    if (s <= bound) {
-      float d = ex::cie94_c(L, a, b, C, q0.y, q1.x, q1.y, q0.w);
-      if (d < best) {
-        best = d;
-        found = j;
+// Any table length (kp = multiple of 8, padded with MASKED entries): centroids are visited in
+// chunks of 8; only each chunk's minimum is kept (3-input-min tournament) together with the best
+// and second-best chunk minima.  The precise certificate then runs on the winning chunk alone, so
+// the half-rate ALU pipe sees ~1.1 min/select operations per (pixel, centroid) instead of 5 and
+// the loop is bound by the 5 FMAs of the score.
+template <int P, bool CONV>
+__device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
+                                               float lmax, float cmax, const float (&econv)[P],
+                                               const float (&pconst)[P], float (&eps)[P], unsigned int (&idx)[P],
+                                               bool (&certified)[P]) {
+  static_assert(P % 2 == 0, "pairs of pixels");
+  constexpr int H = P / 2;
+  fast::PixCoef pc[P];
+  fast::f32x2 pp[H][5];
+#pragma unroll
+  for (int i = 0; i < P; ++i) pc[i] = fast::pix_coef(px.L[i], px.a[i], px.b[i], px.C[i]);
+#pragma unroll
+  for (int h = 0; h < H; ++h) pack_coefs(pc[2 * h], pc[2 * h + 1], pp[h]);
+  float m1c[P], m2c[P];
+  unsigned int ic[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    m1c[i] = 3.0e38f;
+    m2c[i] = 3.0e38f;
+    ic[i] = 0;
+  }
+  for (unsigned int c = 0; c < kp; c += 8) {
+    fast::f32x2 s2[8][H];
+#pragma unroll
+    float f[48];
+    load_chunk(rec_at(tab, c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) s2[j][h] = score2(pp[h], f + 6 * j);
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float sa[8], sb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fast::unpack2(s2[j][h], sa[j], sb[j]);
+      const float cm[2] = {tournament8(sa), tournament8(sb)};
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = 2 * h + q;
+        m2c[i] = fminf(m2c[i], fmaxf(cm[q], m1c[i]));
+        const bool lt = cm[q] < m1c[i];
+        m1c[i] = lt ? cm[q] : m1c[i];
+        ic[i] = lt ? c : ic[i];
       }
     }
   }
-  return found;
+  // precise certificate + index inside the winning chunk (per-lane table addresses)
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    float sa[8], sb[8];
+    {
+      float f[48];
+      load_chunk(rec_at(tab, ic[2 * h]), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sa[j] = score1(pc[2 * h], f + 6 * j);
+      load_chunk(rec_at(tab, ic[2 * h + 1]), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sb[j] = score1(pc[2 * h + 1], f + 6 * j);
+    }
+    const float ma = tournament8(sa), mb = tournament8(sb);
+    const float ea = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, econv[2 * h], pconst[2 * h]);
+    const float eb = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, econv[2 * h + 1],
+                                     pconst[2 * h + 1]);
+    bool ca, cb;
+    unsigned int ia, ib;
+    certify_pair<8>(sa, sb, ma, mb, ea, eb, ca, cb, ia, ib);
+    eps[2 * h] = ea;
+    eps[2 * h + 1] = eb;
+    certified[2 * h] = ca && (m2c[2 * h] - ma > ea);
+    certified[2 * h + 1] = cb && (m2c[2 * h + 1] - mb > eb);
+    idx[2 * h] = ic[2 * h] + ia;
+    idx[2 * h + 1] = ic[2 * h + 1] + ib;
+  }
+}
+
+// Exact re-evaluation, warp-cooperative.  Every lane of the warp must call this together (the
+// callers' loops are warp-uniform).  For each lane whose `need` flag is set, the 32 lanes split the
+// centroid range (j = lane, lane+32, ...): they find the pixel's smallest fast score, then evaluate
+// the exact reference distance (delta_e.wgsl:1-22 order, IEEE) for every centroid whose fast score
+// lies within `slack` of it, and reduce the 64-bit key (distance bits << 32 | index) with a min.
+// The minimum of that key is the lowest index among the smallest distances, i.e. exactly the
+// result of the reference's in-order scan with strict '<' starting from (100000.0, index 0)
+// (find_centroid.wgsl:29-41).  (L,a,b,C) must be the exact pixel (C = exact chroma).
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+__device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict__ tab, unsigned int k, bool need,
+                                                       float L, float a, float b, float C, float slack,
+                                                       unsigned int idx_in) {
+  unsigned int mask = __ballot_sync(0xffffffffu, need);
+  const unsigned int lane = threadIdx.x & 31u;
+  unsigned int result = idx_in;
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const float pL = __shfl_sync(0xffffffffu, L, src), pa = __shfl_sync(0xffffffffu, a, src);
+    const float pb = __shfl_sync(0xffffffffu, b, src), pC = __shfl_sync(0xffffffffu, C, src);
+    const float pslack = __shfl_sync(0xffffffffu, slack, src);
+    const fast::PixCoef pc = fast::pix_coef(pL, pa, pb, pC);
+    float m = 3.0e38f;
+    for (unsigned int j = lane; j < k; j += 32) m = fminf(m, score1(pc, rec_at(tab, j)->q));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float bound = m + pslack;
+    unsigned long long best = ~0ull;
+    for (unsigned int j = lane; j < k; j += 32) {
+      const CentRec r = *rec_at(tab, j);
+      if (score1(pc, r.q) <= bound) {
+        const float d = ex::cie94_c(pL, pa, pb, pC, r.q[1], r.q[4], r.q[5], r.q[3]);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | j;
+        best = key < best ? key : best;
+      }
+    }
+    best = warp_min_u64(best);
+    if ((int)lane == src) {
+      const float d = __uint_as_float((unsigned int)(best >> 32));
+      result = (best != ~0ull && d < 100000.0f) ? (unsigned int)(best & 0xffffffffull) : 0u;
+    }
+  }
+  return result;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,11 +587,11 @@ __global__ void k_init_pick(JobPtrs J, const float4* __restrict__ work, unsigned
 // cached work plane: 16 B/px read, nothing written but k x 4 integer sums.
 //
 // Sums are exact integers, rint(v * 2^16) accumulated in int32 thread-private shared-memory slots
-// (ACC_PRIVATE: conflict-free 128-bit read-modify-write, flushed before they can overflow) or sent
-// straight to L2 with 64-bit reductions (ACC_GLOBAL, large k).  Integer addition commutes, so the
-// result is independent of block scheduling, grid size and of how many GPUs share the image.
-// The last block to finish turns the sums into the new centroids, convergence flags and the next
-// table, so a pass is exactly one launch and needs no host round trip.
+// (PRIVATE: conflict-free 128-bit read-modify-write, flushed before they can overflow) or sent
+// straight to L2 with 64-bit reductions into a per-block copy (large k).  Integer addition
+// commutes, so the result is independent of block scheduling, grid size and of how many GPUs share
+// the image.  The last block to finish turns the sums into the new centroids, convergence flags
+// and the next table, so a pass is exactly one launch and needs no host round trip.
 
 template <int THREADS>
 __device__ void finalize_pass(const JobPtrs& J, int color_space, bool distributed_partial) {
@@ -501,24 +604,19 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, bool distribute
   unsigned int conv = 0;
   for (unsigned int c = tid; c < k; c += THREADS) {
     long long s[4] = {0, 0, 0, 0};
-    for (int copy = 0; copy < ACC_COPIES; ++copy) {
+    for (unsigned int copy = 0; copy < J.acc_copies; ++copy) {
       long long* a = J.acc + ((size_t)copy * k + c) * 4;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         s[q] += __ldcg(a + q);
-        if (!distributed_partial) a[q] = 0;
+        if (!distributed_partial || copy > 0) a[q] = 0;
       }
     }
     if (distributed_partial) {
-      // multi-GPU: leave the folded partial in copy 0 for the all-reduce; finalised later
+      // multi-GPU: leave the folded partial in copy 0 for the all-reduce; k_finalize completes it
       long long* a0 = J.acc + (size_t)c * 4;
 #pragma unroll
       for (int q = 0; q < 4; ++q) a0[q] = s[q];
-      for (int copy = 1; copy < ACC_COPIES; ++copy) {
-        long long* a = J.acc + ((size_t)copy * k + c) * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = 0;
-      }
       continue;
     }
 #pragma unroll
@@ -571,14 +669,16 @@ __device__ __forceinline__ void lloyd_load(const float4* __restrict__ work, unsi
   }
 }
 
-template <int KT, int THREADS, int P, bool SAVED, bool CHECK>
-__device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, const float2* __restrict__ s_tab2,
-                                           int4* __restrict__ s_acc,
-                                           const float4 (&v)[P], unsigned long long base, unsigned long long n,
-                                           unsigned int k, float lmax, float cmax, unsigned int tid,
-                                           unsigned int& slow) {
+// One tile of THREADS x P pixels.  KT > 0: compile-time table length (saved-score search);
+// KT == 0: runtime length kp (chunked search).  PRIVATE: thread-private int4 slots in s_acc.
+template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK>
+__device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, unsigned int kp, int4* __restrict__ s_acc,
+                                           unsigned long long* __restrict__ g_acc, const float4 (&v)[P],
+                                           unsigned long long base, unsigned long long n, unsigned int k,
+                                           float lmax, float cmax, unsigned int tid, unsigned int& slow) {
   Pix<P> px;
   bool valid[P];
+  float zero[P];
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     valid[i] = CHECK ? (base + (unsigned long long)i * THREADS) < n : true;
@@ -586,90 +686,89 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
     px.a[i] = v[i].y;
     px.b[i] = v[i].z;
     px.C[i] = v[i].w;
+    zero[i] = 0.0f;
   }
-  float m1[P], eps[P];
+  float eps[P];
   unsigned int idx[P];
   bool certified[P];
-  if (SAVED) {
-    argmin_saved_x2<P, KT>(s_tab2, px, lmax, cmax, m1, eps, idx, certified);
-  } else {
-    float m2[P];
-    argmin_fast<P, KT>(s_tab, KT, px, m1, m2, idx);
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      eps[i] = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
-      certified[i] = m2[i] - m1[i] > eps[i];
-    }
-  }
+  if (KT > 0)
+    argmin_small<P, (KT > 0 ? KT : 8), false>(s_tab, px, lmax, cmax, zero, zero, eps, idx, certified);
+  else
+    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, zero, zero, eps, idx, certified);
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    if (!certified[i] && valid[i]) {
-      idx[i] = argmin_exact(s_tab, k, px.L[i], px.a[i], px.b[i], px.C[i], m1[i] + eps[i]);
-      ++slow;
+    const bool need = !certified[i] && valid[i];
+    if (__any_sync(0xffffffffu, need)) {
+      idx[i] = warp_exact_argmin(s_tab, k, need, px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
+      slow += need ? 1u : 0u;
     }
   }
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     if (valid[i]) {
-      int4* slot = s_acc + idx[i] * THREADS + tid;
-      int4 a = *slot;
-      a.x += ex::to_fixed(px.L[i]);
-      a.y += ex::to_fixed(px.a[i]);
-      a.z += ex::to_fixed(px.b[i]);
-      a.w += 1;
-      *slot = a;
+      if (PRIVATE) {
+        int4* slot = s_acc + idx[i] * THREADS + tid;
+        int4 a = *slot;
+        a.x += ex::to_fixed(px.L[i]);
+        a.y += ex::to_fixed(px.a[i]);
+        a.z += ex::to_fixed(px.b[i]);
+        a.w += 1;
+        *slot = a;
+      } else {
+        unsigned long long* a = g_acc + (size_t)idx[i] * 4;
+        atomicAdd(a + 0, (unsigned long long)(long long)ex::to_fixed(px.L[i]));
+        atomicAdd(a + 1, (unsigned long long)(long long)ex::to_fixed(px.a[i]));
+        atomicAdd(a + 2, (unsigned long long)(long long)ex::to_fixed(px.b[i]));
+        atomicAdd(a + 3, 1ull);
+      }
     }
   }
 }
 
-template <int KT, int THREADS, int P, bool SAVED, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_lloyd_private(JobPtrs J, const float4* __restrict__ work,
-                                                                 unsigned long long n, int color_space,
-                                                                 int distributed_partial) {
-  // KT: compile-time table length (k padded with MASKED entries), fully unrolled.
+// KT > 0: table of KT entries in static shared memory.  KT == 0: table of pad32(k) entries at the
+// start of dynamic shared memory (followed, if PRIVATE, by the accumulator slots for KCAP clusters).
+template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4* __restrict__ work,
+                                                         unsigned long long n, int color_space,
+                                                         int distributed_partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int4* s_acc = reinterpret_cast<int4*>(smem_raw);  // [KT][THREADS]
-  __shared__ CentRec s_tab[KT];
-  __shared__ __align__(16) float2 s_tab2[KT * 6];  // the same table as duplicated pairs for FFMA2
+  __shared__ __align__(16) unsigned char s_tab_static[KT > 0 ? (KT / 8) * CHUNK_BYTES : 16];
   __shared__ bool s_last;
   JobState* st = J.st;
   if (st->done) return;
   const unsigned int tid = threadIdx.x;
   const unsigned int k = st->k;
-  for (unsigned int c = tid; c < KT; c += THREADS) {
-    CentRec r = J.tab[c];
-    s_tab[c] = r;
-    s_tab2[c * 6 + 0] = make_float2(r.q0.x, r.q0.x);
-    s_tab2[c * 6 + 1] = make_float2(r.q0.y, r.q0.y);
-    s_tab2[c * 6 + 2] = make_float2(r.q0.z, r.q0.z);
-    s_tab2[c * 6 + 3] = make_float2(r.q0.w, r.q0.w);
-    s_tab2[c * 6 + 4] = make_float2(r.q1.x, r.q1.x);
-    s_tab2[c * 6 + 5] = make_float2(r.q1.y, r.q1.y);
+  const unsigned int kp = KT > 0 ? (unsigned int)KT : pad32(k);
+  CentRec* s_tab = reinterpret_cast<CentRec*>(KT > 0 ? s_tab_static : smem_raw);
+  int4* s_acc = reinterpret_cast<int4*>(smem_raw + (KT > 0 ? 0 : tab_smem_bytes(pad32(KCAP))));  // [KCAP][THREADS]
+  tab_to_smem(s_tab, J.tab, kp, tid, THREADS);
+  if (PRIVATE) {
+#pragma unroll 4
+    for (int c = 0; c < KCAP; ++c) s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
   }
-#pragma unroll
-  for (int c = 0; c < KT; ++c) s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
   const float lmax = st->lmax, cmax = st->cmax;
   __syncthreads();
 
   constexpr unsigned long long TILE = (unsigned long long)THREADS * P;
   const unsigned long long full_tiles = n / TILE;
+  unsigned long long* g_acc = reinterpret_cast<unsigned long long*>(J.acc + (size_t)(blockIdx.x % J.acc_copies) * k * 4);
   unsigned int since_flush = 0;
   unsigned int slow = 0;
 
   auto flush = [&]() {
+    if (!PRIVATE) return;
     // Every warp folds the private slots of its own 32 threads for all clusters (no block sync
     // needed: a warp only reads what it wrote) and sends 4 reductions per cluster to L2.
     const unsigned int lane = tid & 31;
-    long long* dst = J.acc + (size_t)(blockIdx.x % ACC_COPIES) * k * 4;
     for (unsigned int c = 0; c < k; ++c) {
       int4 v = s_acc[c * THREADS + tid];
       s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
       long long s0 = warp_sum_i64(v.x), s1 = warp_sum_i64(v.y), s2 = warp_sum_i64(v.z), s3 = warp_sum_i64(v.w);
       if (lane == 0 && s3 != 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 4 + 0), (unsigned long long)s0);
-        atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 4 + 1), (unsigned long long)s1);
-        atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 4 + 2), (unsigned long long)s2);
-        atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 4 + 3), (unsigned long long)s3);
+        atomicAdd(g_acc + c * 4 + 0, (unsigned long long)s0);
+        atomicAdd(g_acc + c * 4 + 1, (unsigned long long)s1);
+        atomicAdd(g_acc + c * 4 + 2, (unsigned long long)s2);
+        atomicAdd(g_acc + c * 4 + 3, (unsigned long long)s3);
       }
     }
     since_flush = 0;
@@ -684,20 +783,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd_private(JobPtrs J, cons
     for (; tile < full_tiles; tile += gridDim.x) {
       const unsigned long long next = tile + gridDim.x;
       if (next < full_tiles) lloyd_load<THREADS, P, false>(work, next * TILE + tid, n, nxt);
-      lloyd_tile<KT, THREADS, P, SAVED, false>(s_tab, s_tab2, s_acc, cur, tile * TILE + tid, n, k, lmax, cmax, tid, slow);
+      lloyd_tile<KT, THREADS, P, PRIVATE, false>(s_tab, kp, s_acc, g_acc, cur, tile * TILE + tid, n, k, lmax, cmax, tid,
+                                                 slow);
       since_flush += P;
       // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
-      if (since_flush + P > 240) flush();
+      if (PRIVATE && since_flush + P > 240) flush();
 #pragma unroll
       for (int i = 0; i < P; ++i) cur[i] = nxt[i];
     }
   }
   // ragged tail (< TILE pixels), taken by the block whose turn it would be
   if (full_tiles * TILE < n && blockIdx.x == (unsigned int)(full_tiles % gridDim.x)) {
-    if (since_flush + P > 240) flush();
+    if (PRIVATE && since_flush + P > 240) flush();
     float4 tail[P];
     lloyd_load<THREADS, P, true>(work, full_tiles * TILE + tid, n, tail);
-    lloyd_tile<KT, THREADS, P, SAVED, true>(s_tab, s_tab2, s_acc, tail, full_tiles * TILE + tid, n, k, lmax, cmax, tid, slow);
+    lloyd_tile<KT, THREADS, P, PRIVATE, true>(s_tab, kp, s_acc, g_acc, tail, full_tiles * TILE + tid, n, k, lmax, cmax,
+                                              tid, slow);
   }
   flush();
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
@@ -712,77 +813,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd_private(JobPtrs J, cons
   }
 }
 
-// Large k: table in dynamic shared memory, runtime loop, sums reduced straight into L2.
-template <int THREADS, int P>
-__global__ void __launch_bounds__(THREADS) k_lloyd_global(JobPtrs J, const float4* __restrict__ work,
-                                                          unsigned long long n, int color_space,
-                                                          int distributed_partial) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CentRec* s_tab = reinterpret_cast<CentRec*>(smem_raw);
-  __shared__ bool s_last;
-  JobState* st = J.st;
-  if (st->done) return;
-  const unsigned int tid = threadIdx.x;
-  const unsigned int k = st->k;
-  const unsigned int kp = pad32(k);
-  for (unsigned int c = tid; c < kp; c += THREADS) s_tab[c] = J.tab[c];
-  const float lmax = st->lmax, cmax = st->cmax;
-  __syncthreads();
-
-  constexpr unsigned long long TILE = (unsigned long long)THREADS * P;
-  const unsigned long long tiles = (n + TILE - 1) / TILE;
-  unsigned long long* acc = reinterpret_cast<unsigned long long*>(J.acc + (size_t)(blockIdx.x % ACC_COPIES) * k * 4);
-  unsigned int slow = 0;
-  for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const unsigned long long base = tile * TILE + tid;
-    Pix<P> px;
-    bool valid[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      unsigned long long p = base + (unsigned long long)i * THREADS;
-      valid[i] = p < n;
-      float4 v = valid[i] ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-      px.L[i] = v.x;
-      px.a[i] = v.y;
-      px.b[i] = v.z;
-      px.C[i] = v.w;
-    }
-    float m1[P], m2[P];
-    unsigned int idx[P];
-    argmin_fast<P, 4>(s_tab, kp, px, m1, m2, idx);
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      float eps = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
-      if (m2[i] - m1[i] <= eps && valid[i]) {
-        idx[i] = argmin_exact(s_tab, k, px.L[i], px.a[i], px.b[i], px.C[i], m1[i] + eps);
-        ++slow;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      if (valid[i]) {
-        unsigned long long* a = acc + (size_t)idx[i] * 4;
-        atomicAdd(a + 0, (unsigned long long)(long long)ex::to_fixed(px.L[i]));
-        atomicAdd(a + 1, (unsigned long long)(long long)ex::to_fixed(px.a[i]));
-        atomicAdd(a + 2, (unsigned long long)(long long)ex::to_fixed(px.b[i]));
-        atomicAdd(a + 3, 1ull);
-      }
-    }
-  }
-  if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
-
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    finalize_pass<THREADS>(J, color_space, distributed_partial != 0);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// K5 alone: labels for a work plane (stage-level parity test hook, also used by meld-free tools).
+// K5 alone: labels for a work plane (stage-level parity test hook).
 template <int THREADS, int P>
 __global__ void __launch_bounds__(THREADS) k_assign(JobPtrs J, const float4* __restrict__ work,
                                                     unsigned long long n, uint32_t* __restrict__ labels) {
@@ -792,7 +824,7 @@ __global__ void __launch_bounds__(THREADS) k_assign(JobPtrs J, const float4* __r
   const unsigned int tid = threadIdx.x;
   const unsigned int k = st->k;
   const unsigned int kp = pad32(k);
-  for (unsigned int c = tid; c < kp; c += THREADS) s_tab[c] = J.tab[c];
+  tab_to_smem(s_tab, J.tab, kp, tid, THREADS);
   const float lmax = st->lmax, cmax = st->cmax;
   __syncthreads();
   constexpr unsigned long long TILE = (unsigned long long)THREADS * P;
@@ -800,29 +832,31 @@ __global__ void __launch_bounds__(THREADS) k_assign(JobPtrs J, const float4* __r
   unsigned int slow = 0;
   for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const unsigned long long base = tile * TILE + tid;
+    float4 v[P];
+    lloyd_load<THREADS, P, true>(work, base, n, v);
     Pix<P> px;
-    bool valid[P];
+    float zero[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      unsigned long long p = base + (unsigned long long)i * THREADS;
-      valid[i] = p < n;
-      float4 v = valid[i] ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-      px.L[i] = v.x;
-      px.a[i] = v.y;
-      px.b[i] = v.z;
-      px.C[i] = v.w;
+      px.L[i] = v[i].x;
+      px.a[i] = v[i].y;
+      px.b[i] = v[i].z;
+      px.C[i] = v[i].w;
+      zero[i] = 0.0f;
     }
-    float m1[P], m2[P];
+    float eps[P];
     unsigned int idx[P];
-    argmin_fast<P, 4>(s_tab, kp, px, m1, m2, idx);
+    bool certified[P];
+    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, zero, zero, eps, idx, certified);
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      float eps = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
-      if (m2[i] - m1[i] <= eps && valid[i]) {
-        idx[i] = argmin_exact(s_tab, k, px.L[i], px.a[i], px.b[i], px.C[i], m1[i] + eps);
-        ++slow;
+      const bool valid = base + (unsigned long long)i * THREADS < n;
+      const bool need = !certified[i] && valid;
+      if (__any_sync(0xffffffffu, need)) {
+        idx[i] = warp_exact_argmin(s_tab, k, need, px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
+        slow += need ? 1u : 0u;
       }
-      if (valid[i]) labels[base + (unsigned long long)i * THREADS] = idx[i];
+      if (valid) labels[base + (unsigned long long)i * THREADS] = idx[i];
     }
   }
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
@@ -838,35 +872,25 @@ __global__ void __launch_bounds__(THREADS) k_assign(JobPtrs J, const float4* __r
 __device__ __constant__ float c_bayer[16] = {0.f, 8.f, 2.f, 10.f, 12.f, 4.f, 14.f, 6.f,
                                              3.f, 11.f, 1.f, 9.f, 15.f, 7.f, 13.f, 5.f};
 
-template <int MODE, int KT>
-__device__ __noinline__ unsigned int remap_exact(const CentRec* __restrict__ tab, unsigned int k, uint32_t v,
-                                                 const float* __restrict__ lut, int color_space, float off,
-                                                 float slack) {
+// Exact pixel of the remap kernels: Lab through the FP64 pow path (+ the dither offset).
+template <int MODE>
+__device__ __noinline__ float4 remap_exact_pixel(uint32_t v, const float* __restrict__ lut, int color_space, float off) {
   float4 e = color_space == 0 ? ex::lin100_to_lab(lut[v & 255u], lut[(v >> 8) & 255u], lut[(v >> 16) & 255u])
                               : ex::rgb8_to_rgbf(v);
-  float L = e.x, a = e.y, b = e.z, C = e.w;
   if (MODE == 1) {  // mix_colors.wgsl:70-72
-    L = fadd(L, off);
-    a = fadd(a, off);
-    b = fadd(b, off);
-    C = ex::chroma(a, b);
+    e.x = fadd(e.x, off);
+    e.y = fadd(e.y, off);
+    e.z = fadd(e.z, off);
+    e.w = ex::chroma(e.y, e.z);
   }
-  // candidate bound around this pixel's own best fast score
-  fast::PixCoef pc = fast::pix_coef(L, a, b, C);
-  float m1 = 3.0e38f;
-  for (unsigned int j = 0; j < k; ++j) {
-    const float4 q0 = tab[j].q0;
-    const float4 q1 = tab[j].q1;
-    m1 = fminf(m1, fast::score(pc, q0, make_float2(q1.x, q1.y)));
-  }
-  return argmin_exact(tab, k, L, a, b, C, m1 + slack);
+  return e;
 }
 
 template <int MODE, int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_remap(JobPtrs J, const uint32_t* __restrict__ rgba, unsigned int w,
+__global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t* __restrict__ rgba, unsigned int w,
                                                    unsigned long long n, int color_space,
                                                    const float* __restrict__ lut_g, uint32_t* __restrict__ out) {
-  // KT > 0: compile-time table length; KT == 0: runtime length in dynamic shared memory.
+  // KT > 0: compile-time table length; KT == 0: runtime length.  Table + palette in dynamic smem.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CentRec* s_tab = reinterpret_cast<CentRec*>(smem_raw);
   __shared__ float lut[256];
@@ -874,11 +898,9 @@ __global__ void __launch_bounds__(THREADS) k_remap(JobPtrs J, const uint32_t* __
   const unsigned int tid = threadIdx.x;
   const unsigned int k = st->k;
   const unsigned int kp = KT > 0 ? (unsigned int)KT : pad32(k);
-  uint32_t* s_pal = reinterpret_cast<uint32_t*>(s_tab + kp);
-  for (unsigned int c = tid; c < kp; c += THREADS) {
-    s_tab[c] = J.tab[c];
-    s_pal[c] = c < k ? J.pal[c] : 0u;
-  }
+  uint32_t* s_pal = reinterpret_cast<uint32_t*>(smem_raw + tab_smem_bytes(kp));
+  tab_to_smem(s_tab, J.tab, kp, tid, THREADS);
+  for (unsigned int c = tid; c < kp; c += THREADS) s_pal[c] = c < k ? J.pal[c] : 0u;
   for (unsigned int c = tid; c < 256; c += THREADS) lut[c] = lut_g[c];
   const float lmax = st->lmax, cmax = st->cmax;
   const float thr = st->dither_threshold;
@@ -888,10 +910,13 @@ __global__ void __launch_bounds__(THREADS) k_remap(JobPtrs J, const uint32_t* __
   const unsigned long long groups = (n + P - 1) / P;
   const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
   unsigned int slow = 0;
-  for (unsigned long long g = (unsigned long long)blockIdx.x * THREADS + tid; g < groups; g += stride) {
+  // warp-uniform trip count (the exact path is warp-cooperative); lanes past the end idle
+  for (unsigned long long g0 = (unsigned long long)blockIdx.x * THREADS; g0 < groups; g0 += stride) {
+    const unsigned long long g = g0 + tid;
     const unsigned long long p0 = g * P;
+    const bool live = g < groups;
     uint32_t v[P];
-    const bool full = p0 + P <= n;
+    const bool full = live && p0 + P <= n;
     if (full && (reinterpret_cast<uintptr_t>(rgba) & 15) == 0) {
       uint4 t = __ldcs(reinterpret_cast<const uint4*>(rgba) + g);
       v[0] = t.x;
@@ -900,13 +925,10 @@ __global__ void __launch_bounds__(THREADS) k_remap(JobPtrs J, const uint32_t* __
       v[3] = t.w;
     } else {
 #pragma unroll
-      for (int i = 0; i < P; ++i) v[i] = p0 + i < n ? rgba[p0 + i] : 0u;
-    }
-    if (MODE != 1 && k == 1) {
-      // single colour: the scan trivially returns index 0
+      for (int i = 0; i < P; ++i) v[i] = (live && p0 + i < n) ? rgba[p0 + i] : 0u;
     }
     Pix<P> px;
-    float off[P];
+    float off[P], econv[P], pconst[P];
     unsigned int x = 0, y = 0;
     if (MODE == 1) {
       x = (unsigned int)(p0 % w);
@@ -943,37 +965,37 @@ __global__ void __launch_bounds__(THREADS) k_remap(JobPtrs J, const uint32_t* __
       px.a[i] = a;
       px.b[i] = b;
       px.C[i] = sqrtf(fmaf(a, a, b * b));
+      const float SC = fmaf(0.045f, px.C[i], 1.0f);
+      const float rSC = fast::rcp(SC);
+      pconst[i] = fmaf(L, L, (px.C[i] * rSC) * (px.C[i] * rSC));
+      econv[i] = (color_space == 0 ? 5.0f * fast::LAB_ERR : 5.0f * 2.4e-7f) * SC;
     }
-    float m1[P], m2[P];
+    float eps[P];
     unsigned int idx[P];
+    bool certified[P];
     if (KT > 0)
-      argmin_fast<P, (KT > 0 ? KT : 4)>(s_tab, kp, px, m1, m2, idx);
+      argmin_small<P, (KT > 0 ? KT : 8), true>(s_tab, px, lmax, cmax, econv, pconst, eps, idx, certified);
     else
-      argmin_fast<P, 4>(s_tab, kp, px, m1, m2, idx);
+      argmin_chunked<P, true>(s_tab, kp, px, lmax, cmax, econv, pconst, eps, idx, certified);
     uint32_t o[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      // error bound: score rounding + sensitivity of the score gap to the approximate Lab:
-      // |grad d^2| <= 2.5 * D_E, D_E <= SC * d, two candidates -> 5 * SC * d * LAB_ERR.
-      float eps = fast::score_eps(px.L[i], px.C[i], lmax, cmax);
-      float SC = fmaf(0.045f, px.C[i], 1.0f);
-      float pconst = fmaf(px.L[i], px.L[i], (px.C[i] * px.C[i]) / (SC * SC));
-      float d2 = fmaxf(m1[i] + pconst, 0.0f) + eps;
-      float eps_conv = color_space == 0 ? 5.0f * fast::LAB_ERR * SC * sqrtf(d2) + 3.0f * fast::LAB_ERR * fast::LAB_ERR
-                                        : 5.0f * 2.4e-7f * SC * sqrtf(d2);
-      float slack = eps + eps_conv;
-      if (m2[i] - m1[i] <= slack && p0 + i < n && k > 1) {
-        idx[i] = remap_exact<MODE, KT>(s_tab, k, v[i], lut, color_space, off[i], 2.0f * slack);
-        ++slow;
+      const bool need = !certified[i] && live && p0 + i < n && k > 1;
+      if (__any_sync(0xffffffffu, need)) {
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (need) e = remap_exact_pixel<MODE>(v[i], lut, color_space, off[i]);
+        // the exact pixel is used here, so only the score-rounding part of the bound is needed
+        idx[i] = warp_exact_argmin(s_tab, k, need, e.x, e.y, e.z, e.w, fast::score_eps(e.x, e.w, lmax, cmax), idx[i]);
+        slow += need ? 1u : 0u;
       }
-      o[i] = s_pal[idx[i]];
+      o[i] = s_pal[k > 1 ? idx[i] : 0u];
     }
     if (full && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
       __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4(o[0], o[1], o[2], o[3]));
     } else {
 #pragma unroll
       for (int i = 0; i < P; ++i)
-        if (p0 + i < n) out[p0 + i] = o[i];
+        if (live && p0 + i < n) out[p0 + i] = o[i];
     }
   }
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
