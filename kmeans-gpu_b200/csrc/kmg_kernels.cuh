@@ -275,26 +275,33 @@ __device__ __forceinline__ void load_chunk(const CentRec* chunk, float (&f)[48])
 
 // Error bound of a score gap.  CONV (remap kernels): the pixel itself is approximate (fast Lab),
 // so the gap may additionally move by |grad d^2| * LAB_ERR summed over the two candidates:
-// |grad d^2| <= 2.5 * D_E, D_E <= SC * d  =>  econv * sqrt(d^2) with econv = 5 * LAB_ERR * SC and
-// d^2 = best score + the pixel-only part of the squared distance (pconst).
+// |grad d^2| <= 2.5 * D_E, D_E <= SC * d  =>  conv_k * SC * sqrt(d^2) with conv_k = 5 * LAB_ERR and
+// d^2 = best score + the pixel-only part of the squared distance, L^2 + C^2 / SC^2.
 template <bool CONV>
-__device__ __forceinline__ float total_eps(float eps0, float m, float econv, float pconst) {
+__device__ __forceinline__ float total_eps(float eps0, float m, float conv_k, float L, float C, float inv_sc2) {
   if (!CONV) return eps0;
-  return eps0 + econv * sqrtf(fmaxf(m + pconst, 0.0f) + eps0) + 3.0e-6f;
+  const float pconst = fmaf(L, L, C * C * inv_sc2);
+  const float SC = fmaf(0.045f, C, 1.0f);
+  return eps0 + conv_k * SC * fast::sqrt_approx(fmaxf(m + pconst, 0.0f) + eps0) + 3.0e-6f;
 }
 
 // Small tables (KT = 8 or 16, compile time): all KT scores of a pixel stay in registers.
 template <int P, int KT, bool CONV>
 __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, const Pix<P>& px, float lmax,
-                                             float cmax, const float (&econv)[P], const float (&pconst)[P],
-                                             float (&eps)[P], unsigned int (&idx)[P], bool (&certified)[P]) {
+                                             float cmax, float conv_k, float (&eps)[P], unsigned int (&idx)[P],
+                                             bool (&certified)[P]) {
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::f32x2 pp[H][5];
+  float inv_sc2[P];
 #pragma unroll
-  for (int h = 0; h < H; ++h)
-    pack_coefs(fast::pix_coef(px.L[2 * h], px.a[2 * h], px.b[2 * h], px.C[2 * h]),
-               fast::pix_coef(px.L[2 * h + 1], px.a[2 * h + 1], px.b[2 * h + 1], px.C[2 * h + 1]), pp[h]);
+  for (int h = 0; h < H; ++h) {
+    const fast::PixCoef c0 = fast::pix_coef(px.L[2 * h], px.a[2 * h], px.b[2 * h], px.C[2 * h]);
+    const fast::PixCoef c1 = fast::pix_coef(px.L[2 * h + 1], px.a[2 * h + 1], px.b[2 * h + 1], px.C[2 * h + 1]);
+    inv_sc2[2 * h] = c0.p1;
+    inv_sc2[2 * h + 1] = c1.p1;
+    pack_coefs(c0, c1, pp[h]);
+  }
   fast::f32x2 s2[KT][H];
 #pragma unroll
   for (int c = 0; c < KT; c += 8) {
@@ -319,9 +326,10 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
     }
     ma = fminf(ma, sa[KT - 1]);
     mb = fminf(mb, sb[KT - 1]);
-    eps[2 * h] = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, econv[2 * h], pconst[2 * h]);
-    eps[2 * h + 1] = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, econv[2 * h + 1],
-                                     pconst[2 * h + 1]);
+    eps[2 * h] = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, conv_k, px.L[2 * h],
+                                 px.C[2 * h], inv_sc2[2 * h]);
+    eps[2 * h + 1] = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, conv_k,
+                                     px.L[2 * h + 1], px.C[2 * h + 1], inv_sc2[2 * h + 1]);
     certify_pair<KT>(sa, sb, ma, mb, eps[2 * h], eps[2 * h + 1], certified[2 * h], certified[2 * h + 1], idx[2 * h],
                      idx[2 * h + 1]);
   }
@@ -334,9 +342,8 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
 // the loop is bound by the 5 FMAs of the score.
 template <int P, bool CONV>
 __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
-                                               float lmax, float cmax, const float (&econv)[P],
-                                               const float (&pconst)[P], float (&eps)[P], unsigned int (&idx)[P],
-                                               bool (&certified)[P]) {
+                                               float lmax, float cmax, float conv_k, float (&eps)[P],
+                                               unsigned int (&idx)[P], bool (&certified)[P]) {
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::PixCoef pc[P];
@@ -393,9 +400,10 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
       for (int j = 0; j < 8; ++j) sb[j] = score1(pc[2 * h + 1], f + 6 * j);
     }
     const float ma = tournament8(sa), mb = tournament8(sb);
-    const float ea = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, econv[2 * h], pconst[2 * h]);
-    const float eb = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, econv[2 * h + 1],
-                                     pconst[2 * h + 1]);
+    const float ea = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, conv_k, px.L[2 * h],
+                                     px.C[2 * h], pc[2 * h].p1);
+    const float eb = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, conv_k,
+                                     px.L[2 * h + 1], px.C[2 * h + 1], pc[2 * h + 1].p1);
     bool ca, cb;
     unsigned int ia, ib;
     certify_pair<8>(sa, sb, ma, mb, ea, eb, ca, cb, ia, ib);
@@ -678,7 +686,6 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
                                            float lmax, float cmax, unsigned int tid, unsigned int& slow) {
   Pix<P> px;
   bool valid[P];
-  float zero[P];
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     valid[i] = CHECK ? (base + (unsigned long long)i * THREADS) < n : true;
@@ -686,15 +693,14 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
     px.a[i] = v[i].y;
     px.b[i] = v[i].z;
     px.C[i] = v[i].w;
-    zero[i] = 0.0f;
   }
   float eps[P];
   unsigned int idx[P];
   bool certified[P];
   if (KT > 0)
-    argmin_small<P, (KT > 0 ? KT : 8), false>(s_tab, px, lmax, cmax, zero, zero, eps, idx, certified);
+    argmin_small<P, (KT > 0 ? KT : 8), false>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
   else
-    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, zero, zero, eps, idx, certified);
+    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const bool need = !certified[i] && valid[i];
@@ -835,19 +841,17 @@ __global__ void __launch_bounds__(THREADS) k_assign(JobPtrs J, const float4* __r
     float4 v[P];
     lloyd_load<THREADS, P, true>(work, base, n, v);
     Pix<P> px;
-    float zero[P];
-#pragma unroll
+  #pragma unroll
     for (int i = 0; i < P; ++i) {
       px.L[i] = v[i].x;
       px.a[i] = v[i].y;
       px.b[i] = v[i].z;
       px.C[i] = v[i].w;
-      zero[i] = 0.0f;
-    }
+      }
     float eps[P];
     unsigned int idx[P];
     bool certified[P];
-    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, zero, zero, eps, idx, certified);
+    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       const bool valid = base + (unsigned long long)i * THREADS < n;
@@ -910,14 +914,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t*
   const unsigned long long groups = (n + P - 1) / P;
   const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
   unsigned int slow = 0;
-  // warp-uniform trip count (the exact path is warp-cooperative); lanes past the end idle
-  for (unsigned long long g0 = (unsigned long long)blockIdx.x * THREADS; g0 < groups; g0 += stride) {
-    const unsigned long long g = g0 + tid;
+  const bool aligned = (reinterpret_cast<uintptr_t>(rgba) & 15) == 0;
+  auto load_group = [&](unsigned long long g, uint32_t (&v)[P]) {
     const unsigned long long p0 = g * P;
-    const bool live = g < groups;
-    uint32_t v[P];
-    const bool full = live && p0 + P <= n;
-    if (full && (reinterpret_cast<uintptr_t>(rgba) & 15) == 0) {
+    if (g < groups && p0 + P <= n && aligned) {
       uint4 t = __ldcs(reinterpret_cast<const uint4*>(rgba) + g);
       v[0] = t.x;
       v[1] = t.y;
@@ -925,10 +925,21 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t*
       v[3] = t.w;
     } else {
 #pragma unroll
-      for (int i = 0; i < P; ++i) v[i] = (live && p0 + i < n) ? rgba[p0 + i] : 0u;
+      for (int i = 0; i < P; ++i) v[i] = (g < groups && p0 + i < n) ? rgba[p0 + i] : 0u;
     }
+  };
+  // warp-uniform trip count (the exact path is warp-cooperative); lanes past the end idle.
+  // The next group's pixels are loaded before the current group is processed.
+  uint32_t v[P], vn[P];
+  load_group((unsigned long long)blockIdx.x * THREADS + tid, v);
+  for (unsigned long long g0 = (unsigned long long)blockIdx.x * THREADS; g0 < groups; g0 += stride) {
+    const unsigned long long g = g0 + tid;
+    const unsigned long long p0 = g * P;
+    const bool live = g < groups;
+    const bool full = live && p0 + P <= n;
+    load_group(g + stride, vn);
     Pix<P> px;
-    float off[P], econv[P], pconst[P];
+    float off[P];
     unsigned int x = 0, y = 0;
     if (MODE == 1) {
       x = (unsigned int)(p0 % w);
@@ -964,19 +975,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t*
       px.L[i] = L;
       px.a[i] = a;
       px.b[i] = b;
-      px.C[i] = sqrtf(fmaf(a, a, b * b));
-      const float SC = fmaf(0.045f, px.C[i], 1.0f);
-      const float rSC = fast::rcp(SC);
-      pconst[i] = fmaf(L, L, (px.C[i] * rSC) * (px.C[i] * rSC));
-      econv[i] = (color_space == 0 ? 5.0f * fast::LAB_ERR : 5.0f * 2.4e-7f) * SC;
+      px.C[i] = fast::sqrt_approx(fmaf(a, a, b * b));
     }
+    const float conv_k = color_space == 0 ? 5.0f * fast::LAB_ERR : 5.0f * 2.4e-7f;
     float eps[P];
     unsigned int idx[P];
     bool certified[P];
     if (KT > 0)
-      argmin_small<P, (KT > 0 ? KT : 8), true>(s_tab, px, lmax, cmax, econv, pconst, eps, idx, certified);
+      argmin_small<P, (KT > 0 ? KT : 8), true>(s_tab, px, lmax, cmax, conv_k, eps, idx, certified);
     else
-      argmin_chunked<P, true>(s_tab, kp, px, lmax, cmax, econv, pconst, eps, idx, certified);
+      argmin_chunked<P, true>(s_tab, kp, px, lmax, cmax, conv_k, eps, idx, certified);
     uint32_t o[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -997,6 +1005,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t*
       for (int i = 0; i < P; ++i)
         if (live && p0 + i < n) out[p0 + i] = o[i];
     }
+#pragma unroll
+    for (int i = 0; i < P; ++i) v[i] = vn[i];
   }
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
 }

@@ -134,6 +134,22 @@ __device__ __forceinline__ float rcp(float x) {
   return r;
 }
 
+__device__ __forceinline__ float lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Blackwell packed-f32x2 arithmetic (SASS FFMA2 / FADD2): one issue slot, two lanes of work.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -202,8 +218,8 @@ __device__ __forceinline__ float score_eps(float L, float C1, float lmax, float 
 
 // Approximate f(t) of xyz_to_lab: relative error <= ~2^-21.
 __device__ __forceinline__ float lab_f(float t) {
-  float lg = __log2f(t);
-  float y0 = exp2f(lg * 0.33333334f);
+  float lg = lg2(t);
+  float y0 = ex2(lg * 0.33333334f);
   // one Newton step for the cube root, then the (1/3)_f32 vs 1/3 exponent correction
   float r = rcp(y0 * y0);
   float y1 = fmaf(y0, 0.6666667f, 0.33333334f * t * r);
