@@ -18,8 +18,8 @@
 
 namespace kmg {
 
-// One centroid as the kernels see it: the six constants of the reduced score,
-//   q = {Lc^2, Lc, C2^2, C2, ac, bc}   (24 bytes, records are dense: 8 of them = twelve float4).
+// One centroid as the kernels see it: the six constants of the reduced (half-distance) score,
+//   q = {Lc^2/2, -Lc, C2^2/2, C2, -ac, -bc}   (24 bytes, records are dense: 8 of them = twelve float4).
 // Packed FFMA2 takes them as scalar-broadcast operands, so nothing is duplicated.  Duplicates of
 // a lower-index centroid and padding entries carry q[0] = MASKED so they can never win (the
 // reference's strict '<' scan keeps the lowest index on exact ties anyway).
@@ -117,12 +117,12 @@ __device__ void build_table(const JobPtrs& J, unsigned int k, int color_space, b
         float4 u = J.cent[i];
         dup |= (u.x == v.x && u.y == v.y && u.z == v.z);
       }
-      r.q[0] = dup ? MASKED : v.x * v.x;
-      r.q[1] = v.x;
-      r.q[2] = c2 * c2;
+      r.q[0] = dup ? MASKED : 0.5f * (v.x * v.x);
+      r.q[1] = -v.x;
+      r.q[2] = 0.5f * (c2 * c2);
       r.q[3] = c2;
-      r.q[4] = v.y;
-      r.q[5] = v.z;
+      r.q[4] = -v.y;
+      r.q[5] = -v.z;
       lmax = fmaxf(lmax, fabsf(v.x));
       cmax = fmaxf(cmax, c2);
       if (want_palette)
@@ -204,37 +204,38 @@ __device__ __forceinline__ float tournament8(const float (&s)[8]) {
 }
 
 // Certificate + index over KT saved scores of one pixel pair (sa: first pixel, sb: second).
+// Flag t_j = (s_j > m + eps) is an exact 0/1 (FSET on the ALU pipe); the weighted sum
+//   V = sum_j (KT + j) * (1 - t_j) = KT * z + (sum of the indices of the z unflagged scores)
+// is accumulated exactly in the integer range of an f32 sitting on 2^23, two pixels per FFMA2, so
+// the low mantissa bits of the result are V itself: z == 1  <=>  (V & ~(KT-1)) == KT, and then
+// V & (KT-1) is the index of the only score within eps of the minimum, i.e. the certified arg-min.
 template <int KT>
 __device__ __forceinline__ void certify_pair(const float (&sa)[KT], const float (&sb)[KT], float ma, float mb,
                                              float ea, float eb, bool& ca, bool& cb, unsigned int& ia,
                                              unsigned int& ib) {
-  static_assert((KT & (KT - 1)) == 0, "table length must be a power of two");
-  const float ga = fast::rcp(ea), gb = fast::rcp(eb);
-  const float ba = -ma * ga, bb = -mb * gb;
-  fast::f32x2 v[KT];
+  static_assert((KT & (KT - 1)) == 0 && KT <= 64, "table length must be a small power of two");
+  const float ta = ma + ea, tb = mb + eb;
+  constexpr float TOTAL = (float)(KT * KT + KT * (KT - 1) / 2);
+  fast::f32x2 acc0 = fast::pack2(8388608.0f + TOTAL, 8388608.0f + TOTAL);
+  fast::f32x2 acc1 = fast::pack2(0.0f, 0.0f);
 #pragma unroll
-  for (int j = 0; j < KT; ++j)
-    v[j] = fast::pack2(__saturatef(fmaf(sa[j], ga, ba)), __saturatef(fmaf(sb[j], gb, bb)));
-  fast::f32x2 I = fast::pack2(0.0f, 0.0f);
-  float wgt = 1.0f;
-#pragma unroll
-  for (int n = KT; n > 1; n >>= 1) {
-    fast::f32x2 odd = v[1];
-#pragma unroll
-    for (int m = 1; m < n / 2; ++m) odd = fast::add2(odd, v[2 * m + 1]);
-    I = fast::fma2(odd, fast::pack2(wgt, wgt), I);
-    wgt *= 2.0f;
-#pragma unroll
-    for (int m = 0; m < n / 2; ++m) v[m] = fast::add2(v[2 * m], v[2 * m + 1]);
+  for (int j = 0; j < KT; ++j) {
+    const float fa = sa[j] > ta ? 1.0f : 0.0f;
+    const float fb = sb[j] > tb ? 1.0f : 0.0f;
+    const float w = -(float)(KT + j);
+    if (j & 1)
+      acc1 = fast::fma2(fast::pack2(fa, fb), fast::pack2(w, w), acc1);
+    else
+      acc0 = fast::fma2(fast::pack2(fa, fb), fast::pack2(w, w), acc0);
   }
-  float Sa, Sb, Ia, Ib;
-  fast::unpack2(v[0], Sa, Sb);
-  fast::unpack2(I, Ia, Ib);
-  constexpr float TRI = (float)(KT * (KT - 1) / 2);
-  ca = Sa > (float)(KT - 1) - 1.0e-3f;
-  cb = Sb > (float)(KT - 1) - 1.0e-3f;
-  ia = (unsigned int)__float2int_rn(TRI - Ia) & (unsigned int)(KT - 1);
-  ib = (unsigned int)__float2int_rn(TRI - Ib) & (unsigned int)(KT - 1);
+  float Va, Vb;
+  fast::unpack2(fast::add2(acc0, acc1), Va, Vb);
+  const unsigned int ua = __float_as_uint(Va), ub = __float_as_uint(Vb);
+  constexpr unsigned int HI = 0xffffu & ~(unsigned int)(KT - 1);
+  ca = (ua & HI) == (unsigned int)KT;
+  cb = (ub & HI) == (unsigned int)KT;
+  ia = ua & (unsigned int)(KT - 1);
+  ib = ub & (unsigned int)(KT - 1);
 }
 
 __device__ __forceinline__ void pack_coefs(const fast::PixCoef& c0, const fast::PixCoef& c1, fast::f32x2 (&pp)[5]) {
@@ -276,13 +277,14 @@ __device__ __forceinline__ void load_chunk(const CentRec* chunk, float (&f)[48])
 // Error bound of a score gap.  CONV (remap kernels): the pixel itself is approximate (fast Lab),
 // so the gap may additionally move by |grad d^2| * LAB_ERR summed over the two candidates:
 // |grad d^2| <= 2.5 * D_E, D_E <= SC * d  =>  conv_k * SC * sqrt(d^2) with conv_k = 5 * LAB_ERR and
-// d^2 = best score + the pixel-only part of the squared distance, L^2 + C^2 / SC^2.
+// d^2 = 2 * best score + the pixel-only part of the squared distance, L^2 + C^2 / SC^2.  Scores
+// are half distances, so the bound is halved as well.
 template <bool CONV>
 __device__ __forceinline__ float total_eps(float eps0, float m, float conv_k, float L, float C, float inv_sc2) {
   if (!CONV) return eps0;
   const float pconst = fmaf(L, L, C * C * inv_sc2);
   const float SC = fmaf(0.045f, C, 1.0f);
-  return eps0 + conv_k * SC * fast::sqrt_approx(fmaxf(m + pconst, 0.0f) + eps0) + 3.0e-6f;
+  return eps0 + 0.5f * conv_k * SC * fast::sqrt_approx(fmaxf(fmaf(2.0f, m, pconst), 0.0f) + 2.0f * eps0) + 1.5e-6f;
 }
 
 // Small tables (KT = 8 or 16, compile time): all KT scores of a pixel stay in registers.
@@ -455,7 +457,7 @@ __device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict
     for (unsigned int j = lane; j < k; j += 32) {
       const CentRec r = *rec_at(tab, j);
       if (score1(pc, r.q) <= bound) {
-        const float d = ex::cie94_c(pL, pa, pb, pC, r.q[1], r.q[4], r.q[5], r.q[3]);
+        const float d = ex::cie94_c(pL, pa, pb, pC, -r.q[1], -r.q[4], -r.q[5], r.q[3]);
         const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | j;
         best = key < best ? key : best;
       }
@@ -701,12 +703,20 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
     argmin_small<P, (KT > 0 ? KT : 8), false>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
   else
     argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
+  // one vote per tile: the exact path is rare (1e-4 .. 1e-2 of the pixels)
+  bool need[P], any_need = false;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    const bool need = !certified[i] && valid[i];
-    if (__any_sync(0xffffffffu, need)) {
-      idx[i] = warp_exact_argmin(s_tab, k, need, px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
-      slow += need ? 1u : 0u;
+    need[i] = !certified[i] && valid[i];
+    any_need |= need[i];
+  }
+  if (__any_sync(0xffffffffu, any_need)) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      if (__any_sync(0xffffffffu, need[i])) {
+        idx[i] = warp_exact_argmin(s_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
+        slow += need[i] ? 1u : 0u;
+      }
     }
   }
 #pragma unroll

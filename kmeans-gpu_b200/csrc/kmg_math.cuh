@@ -120,8 +120,13 @@ __device__ __forceinline__ uint32_t rgbf_to_rgba8(float r, float g, float b, flo
   return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(w) << 24);
 }
 
-// Fixed-point unit of the centroid sums: rint(v * 2^16) (exact product, one rounding).
-__device__ __forceinline__ int to_fixed(float v) { return __float2int_rn(fmul(v, 65536.0f)); }
+// Fixed-point unit of the centroid sums: rint(v * 2^16) (exact product, one rounding).  The
+// product is formed by adding 16 to the exponent field (integer pipe instead of the FMA pipe):
+// identical to v * 65536.0f for every normal |v| < 2^111; zeros and denormals give values far
+// below 0.5, which round to 0 exactly as the true product does.
+__device__ __forceinline__ int to_fixed(float v) {
+  return __float2int_rn(__int_as_float(__float_as_int(v) + (16 << 23)));
+}
 
 }  // namespace ex
 
@@ -176,10 +181,13 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
   return r;
 }
 
-// Per-pixel coefficients of the reduced CIE94 score (see DESIGN.md "assignment"):
-//   d^2(p,c) = [L^2 + C1^2/SC^2] + Lc^2 + p0*Lc + p1*C2^2 + p2*C2 + p3*ac + p4*bc
-// with p0 = -2L, p1 = 1/SC^2, p2 = 2*C1*(1/SH^2 - 1/SC^2), p3 = -2a/SH^2, p4 = -2b/SH^2,
-// using da^2 + db^2 - dC^2 = 2*(C1*C2 - a*ac - b*bc).  The bracket does not depend on c.
+// Per-pixel coefficients of the reduced CIE94 score (see DESIGN.md "assignment").  With
+//   da^2 + db^2 - dC^2 = 2*(C1*C2 - a*ac - b*bc)
+// half the squared distance is
+//   d^2(p,c)/2 = [L^2/2 + C1^2/(2 SC^2)] + Lc^2/2 + L*(-Lc) + p1*(C2^2/2) + p2*C2 + p3*(-ac) + p4*(-bc)
+// with p1 = 1/SC^2, p2 = C1*(1/SH^2 - 1/SC^2), p3 = a/SH^2, p4 = b/SH^2.  The bracket does not
+// depend on c; the table record of a centroid is {Lc^2/2, -Lc, C2^2/2, C2, -ac, -bc}, so L itself
+// is the first coefficient and no sign or factor 2 is ever applied per pixel (10 operations).
 struct PixCoef {
   float p0, p1, p2, p3, p4;
 };
@@ -191,29 +199,21 @@ __device__ __forceinline__ PixCoef pix_coef(float L, float a, float b, float C1)
   PixCoef p;
   p.p1 = rSC * rSC;
   float hs = rSH * rSH;
-  p.p0 = -2.0f * L;
-  p.p2 = (C1 + C1) * (hs - p.p1);
-  float t = -2.0f * hs;
-  p.p3 = t * a;
-  p.p4 = t * b;
+  p.p0 = L;
+  p.p2 = C1 * (hs - p.p1);
+  p.p3 = hs * a;
+  p.p4 = hs * b;
   return p;
 }
-// Centroid record used by the score: {Lc^2, Lc, C2^2, C2}, {ac, bc, -, -}.
-__device__ __forceinline__ float score(const PixCoef& p, float4 q0, float2 q1) {
-  float s = fmaf(p.p0, q0.y, q0.x);
-  s = fmaf(p.p1, q0.z, s);
-  s = fmaf(p.p2, q0.w, s);
-  s = fmaf(p.p3, q1.x, s);
-  s = fmaf(p.p4, q1.y, s);
-  return s;
-}
-// Absolute error bound of a score difference (rounding of the 5-term FMA chain, of the
-// coefficients, and the reference's own f32 rounding), generous by > 4x:
-//   eps = 2^-18 * [ (|L| + Lmax)^2 + 2 * (C1 + Cmax)^2 ].
+// Absolute error bound of a (half-distance) score difference: rounding of the 5-term FMA chain,
+// of the coefficients, and the reference's own f32 rounding, generous by > 4x:
+//   eps = 2^-19 * [ (|L| + Lmax)^2 + 2 * (C1 + Cmax)^2 ]   (the scale is folded into the two terms).
 __device__ __forceinline__ float score_eps(float L, float C1, float lmax, float cmax) {
-  float u = fabsf(L) + lmax;
-  float v = C1 + cmax;
-  return 3.814697265625e-6f * fmaf(u, u, 2.0f * v * v);
+  constexpr float KU = 0.00138106793f;  // 2^-9.5
+  constexpr float KV = 0.001953125f;    // 2^-9
+  float u = fmaf(fabsf(L), KU, lmax * KU);
+  float v = fmaf(C1, KV, cmax * KV);
+  return fmaf(u, u, v * v);
 }
 
 // Approximate f(t) of xyz_to_lab: relative error <= ~2^-21.
