@@ -51,7 +51,8 @@ typedef enum kmg_reduce_mode { KMG_REPLACE = 0, KMG_DITHER = 1, KMG_MELD = 2 } k
  *   convergence < 0 -> 1.0 for Lab / 0.01 for Rgb (core/src/lib.rs:189-194),
  *   seed fractions 0.5625 / 0.93359375 = rand(42.0), rand(12.0) of
  *   core/shaders/plus_plus_init.wgsl:58-60,161-165 under correctly rounded f32 sin,
- *   seed_x / seed_y = -1 (>= 0 selects an explicit seed pixel on the clustered image). */
+ *   seed_x / seed_y = -1 (>= 0 selects an explicit seed pixel on the clustered image),
+ *   flags 0. */
 typedef struct kmg_opts {
   uint32_t struct_size; /* sizeof(kmg_opts), for forward compatibility */
   uint32_t max_dim;
@@ -62,7 +63,13 @@ typedef struct kmg_opts {
   float seed_y_frac;
   int32_t seed_x;
   int32_t seed_y;
+  uint32_t flags; /* KMG_OPT_* bits, default 0 */
 } kmg_opts;
+
+/* Run the k-means of small (<= 256 x 256 after the shrink) images stage by stage (resize, convert,
+ * one launch per init round and per Lloyd pass) instead of the single fused thread-block-cluster
+ * launch.  Results are bit-identical either way; the flag exists for the parity tests. */
+#define KMG_OPT_NO_FUSED_KMEANS 1u
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 

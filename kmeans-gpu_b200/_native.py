@@ -33,7 +33,11 @@ class KmgOpts(C.Structure):
         ("seed_y_frac", C.c_float),
         ("seed_x", C.c_int32),
         ("seed_y", C.c_int32),
+        ("flags", C.c_uint32),
     ]
+
+
+KMG_OPT_NO_FUSED_KMEANS = 1
 
 
 _u8p = C.POINTER(C.c_uint8)

@@ -18,6 +18,7 @@
 
 #include "../../include/kmeans_gpu.h"
 #include "kmg_kernels.cuh"
+#include "kmg_small.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -35,6 +36,10 @@ using namespace kmg;
 #define LLOYD32 k_lloyd<0, 32, 128, 4, true, 3>
 #define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
 static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
+// Whole-k-means-in-one-launch variants (kmg_small.cuh): <table/accumulator capacity, threads>
+#define SMALL8 k_kmeans_small<8, 256>
+#define SMALL16 k_kmeans_small<16, 256>
+#define SMALL32 k_kmeans_small<32, 128>
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -161,6 +166,10 @@ struct kmg_ctx {
   std::vector<Workspace*> pool;
   std::atomic<uint64_t> launches{0};
   int occ_private8 = 1, occ_private16 = 1, occ_private32 = 1;
+  // fused small-image k-means: dynamic shared memory available per variant (0 = not launchable)
+  // and whether clusters of 8 / 16 CTAs can be scheduled
+  size_t small_dyn[3] = {0, 0, 0};
+  bool small_cluster_ok[3][2] = {{false, false}, {false, false}, {false, false}};
   // multi-GPU
   int n_ranks = 1, rank = 0;
 #if KMG_HAVE_NCCL_HEADER
@@ -261,6 +270,109 @@ static inline int grid_for(kmg_ctx* ctx, unsigned long long items, int per_block
 #define LAUNCHED(ctx) (ctx)->launches.fetch_add(1, std::memory_order_relaxed)
 #define CHECK_LAUNCH() CU(cudaGetLastError())
 
+
+// ------------------------------------------------------------------------------------------------
+// fused small-image k-means (kmg_small.cuh): capability probe, plan, launch
+
+struct SmallPlan {
+  int variant = -1;          // 0: <8,256>, 1: <16,256>, 2: <32,128>
+  unsigned int kcap = 0, threads = 0, csize = 0, ppc = 0;
+  size_t smem = 0;
+};
+static const void* small_fn(int variant) {
+  return variant == 0 ? (const void*)SMALL8 : variant == 1 ? (const void*)SMALL16 : (const void*)SMALL32;
+}
+static const unsigned int SMALL_KCAP[3] = {8, 16, 32};
+static const unsigned int SMALL_THREADS[3] = {256, 256, 128};
+
+static void small_probe(kmg_ctx* ctx, const cudaDeviceProp& prop) {
+  for (int v = 0; v < 3; ++v) {
+    const void* fn = small_fn(v);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    if ((size_t)prop.sharedMemPerBlockOptin <= fa.sharedSizeBytes + 1024) continue;
+    const size_t dyn = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess ||
+        cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    ctx->small_dyn[v] = dyn;
+    for (int c = 0; c < 2; ++c) {
+      const unsigned int csize = c == 0 ? 8u : 16u;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(csize);
+      cfg.blockDim = dim3(SMALL_THREADS[v]);
+      cfg.dynamicSmemBytes = dyn;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = csize;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) == cudaSuccess && n > 0)
+        ctx->small_cluster_ok[v][c] = true;
+      else
+        cudaGetLastError();
+    }
+  }
+}
+
+// Can the image (n clustered pixels, k centroids) run in the fused kernel?  A single image takes
+// the largest cluster (lowest latency); batches take the smallest one that fits (throughput).
+static bool small_plan(kmg_ctx* ctx, unsigned long long n, uint32_t k, uint32_t n_frames, SmallPlan* plan) {
+  if (k > 32 || n == 0 || n > (1ull << 20)) return false;
+  const int v = k <= 8 ? 0 : (k <= 16 ? 1 : 2);
+  if (ctx->small_dyn[v] == 0) return false;
+  const int order_single[2] = {1, 0}, order_batch[2] = {0, 1};
+  const int* order = n_frames > 1 ? order_batch : order_single;
+  for (int o = 0; o < 2; ++o) {
+    const int c = order[o];
+    if (!ctx->small_cluster_ok[v][c]) continue;
+    const unsigned int csize = c == 0 ? 8u : 16u;
+    const unsigned int ppc = (unsigned int)(((n + csize - 1) / csize + 3) & ~3ull);
+    const size_t smem = small_smem_bytes(ppc, SMALL_KCAP[v], SMALL_THREADS[v], csize);
+    if (smem > ctx->small_dyn[v]) continue;
+    plan->variant = v;
+    plan->kcap = SMALL_KCAP[v];
+    plan->threads = SMALL_THREADS[v];
+    plan->csize = csize;
+    plan->ppc = ppc;
+    plan->smem = smem;
+    return true;
+  }
+  return false;
+}
+
+static int launch_small(kmg_ctx* ctx, const SmallPlan& plan, const SmallParams& prm, const JobPtrs& J0, uint32_t n_frames,
+                        cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan.csize * n_frames);
+  cfg.blockDim = dim3(plan.threads);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = plan.csize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (plan.variant == 0)
+    CU(cudaLaunchKernelEx(&cfg, SMALL8, prm, J0));
+  else if (plan.variant == 1)
+    CU(cudaLaunchKernelEx(&cfg, SMALL16, prm, J0));
+  else
+    CU(cudaLaunchKernelEx(&cfg, SMALL32, prm, J0));
+  LAUNCHED(ctx);
+  return KMG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // lifetime
 
@@ -278,6 +390,7 @@ extern "C" void kmg_default_opts(kmg_opts* o) {
   o->seed_y_frac = 0.93359375f;
   o->seed_x = -1;
   o->seed_y = -1;
+  o->flags = 0;
 }
 
 static kmg_opts resolve_opts(const kmg_opts* in) {
@@ -326,6 +439,7 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   CU(cudaFuncSetAttribute(k_remap<0, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<1, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
+  small_probe(ctx, prop);
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, LLOYD8, 256, 8 * 256 * 16));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, LLOYD16, 256, 16 * 256 * 16));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, LLOYD32, 128, LLOYD32_SMEM));
@@ -426,44 +540,74 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   return KMG_OK;
 }
 
+// Grid of a remap launch: x = persistent blocks per frame, y = frames.  A single image gets
+// sms x blocks/SM blocks; a batch shares that budget between its frames (at least 16 per frame so
+// every block still amortises its table load over many pixel groups).
+static dim3 remap_grid(kmg_ctx* ctx, unsigned long long groups, int blocks_per_sm, uint32_t n_frames) {
+  unsigned long long need = std::max<unsigned long long>(1, (groups + 255) / 256);
+  unsigned long long cap = (unsigned long long)ctx->sms * blocks_per_sm;
+  if (n_frames > 1) cap = std::max<unsigned long long>(16, (2 * cap + n_frames - 1) / n_frames);
+  return dim3((unsigned int)std::min(need, cap), n_frames, 1);
+}
+
 template <int MODE>
 static int launch_remap_mode(kmg_job* j, const uint8_t* d_rgba, uint32_t w, unsigned long long n, uint8_t* d_out,
-                             cudaStream_t s) {
+                             uint32_t n_frames, size_t blob_stride, cudaStream_t s) {
   kmg_ctx* ctx = j->ctx;
   const unsigned long long groups = (n + 3) / 4;
   const uint32_t* in = (const uint32_t*)d_rgba;
   uint32_t* out = (uint32_t*)d_out;
   if (j->k <= 8) {
-    int grid = grid_for(ctx, groups, 256, 4);
-    k_remap<MODE, 8, 256><<<grid, 256, tab_smem_bytes(8) + 8 * 4, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+    dim3 grid = remap_grid(ctx, groups, 4, n_frames);
+    k_remap<MODE, 8, 256><<<grid, 256, tab_smem_bytes(8) + 8 * 4, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out, blob_stride);
   } else if (j->k <= 16) {
-    int grid = grid_for(ctx, groups, 256, 4);
-    k_remap<MODE, 16, 256><<<grid, 256, tab_smem_bytes(16) + 16 * 4, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+    dim3 grid = remap_grid(ctx, groups, 4, n_frames);
+    k_remap<MODE, 16, 256><<<grid, 256, tab_smem_bytes(16) + 16 * 4, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out, blob_stride);
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k)) + (size_t)pad32(j->k) * 4;
-    int grid = grid_for(ctx, groups, 256, smem > 100 * 1024 ? 1 : (smem > 60 * 1024 ? 2 : 3));
-    k_remap<MODE, 0, 256><<<grid, 256, smem, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out);
+    dim3 grid = remap_grid(ctx, groups, smem > 100 * 1024 ? 1 : (smem > 60 * 1024 ? 2 : 3), n_frames);
+    k_remap<MODE, 0, 256><<<grid, 256, smem, s>>>(j->P, in, w, n, j->color_space, ctx->d_lut, out, blob_stride);
   }
   LAUNCHED(ctx);
   CHECK_LAUNCH();
   return KMG_OK;
 }
 
+// n_frames > 1: frames of w x h pixels back to back in d_rgba / d_out, their job blobs blob_stride
+// bytes apart starting at j's (all with j's k and colour space).  prepared: table, dither
+// threshold and RGBA8 palette are already in the blob(s) (written by k_kmeans_small).
 static int launch_remap(kmg_job* j, const uint8_t* d_rgba, uint32_t w, uint32_t h, int mode, uint8_t* d_out,
-                        cudaStream_t s) {
+                        cudaStream_t s, bool prepared = false, uint32_t n_frames = 1, size_t blob_stride = 0) {
   const unsigned long long n = (unsigned long long)w * h;
-  TRY(launch_prepare(j, true, s));
-  if (mode == KMG_REPLACE) return launch_remap_mode<0>(j, d_rgba, w, n, d_out, s);
-  if (mode == KMG_DITHER) return launch_remap_mode<1>(j, d_rgba, w, n, d_out, s);
-  if (mode == KMG_MELD) {
-    int grid = grid_for(j->ctx, n, 256, 8);
-    k_remap_meld<<<grid, 256, (size_t)j->k * 16, s>>>(j->P, (const uint32_t*)d_rgba, n, j->color_space, j->ctx->d_lut,
-                                                      (uint32_t*)d_out);
-    LAUNCHED(j->ctx);
-    CHECK_LAUNCH();
-    return KMG_OK;
+  if (!prepared) {
+    if (n_frames != 1) return fail(KMG_ERR_BAD_ARG, "batched remap needs prepared job blobs");
+    TRY(launch_prepare(j, true, s));
   }
-  return fail(KMG_ERR_BAD_ARG, "unknown reduce mode %d", mode);
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += 32768) {  // gridDim.y <= 65535
+    const uint32_t nf = std::min<uint32_t>(32768, n_frames - f0);
+    kmg_job jf = *j;
+    if (f0) {
+      unsigned char* b = (unsigned char*)j->blob + (size_t)f0 * blob_stride;
+      jf.blob = b;
+      job_carve(&jf, b);
+    }
+    const uint8_t* in = d_rgba + (size_t)f0 * n * 4;
+    uint8_t* out = d_out + (size_t)f0 * n * 4;
+    if (mode == KMG_REPLACE) {
+      TRY(launch_remap_mode<0>(&jf, in, w, n, out, nf, blob_stride, s));
+    } else if (mode == KMG_DITHER) {
+      TRY(launch_remap_mode<1>(&jf, in, w, n, out, nf, blob_stride, s));
+    } else if (mode == KMG_MELD) {
+      dim3 grid = remap_grid(j->ctx, n, 8, nf);
+      k_remap_meld<<<grid, 256, (size_t)j->k * 16, s>>>(jf.P, (const uint32_t*)in, n, j->color_space, j->ctx->d_lut,
+                                                       (uint32_t*)out, blob_stride);
+      LAUNCHED(j->ctx);
+      CHECK_LAUNCH();
+    } else {
+      return fail(KMG_ERR_BAD_ARG, "unknown reduce mode %d", mode);
+    }
+  }
+  return KMG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -520,6 +664,8 @@ static int share_colour(kmg_job* j, unsigned int slot, cudaStream_t s) {
 }
 #endif
 
+static int resolve_seed(const kmg_opts& o, uint32_t gw, uint32_t gh, unsigned long long* seed);
+
 static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cudaStream_t s) {
   kmg_ctx* ctx = j->ctx;
   const unsigned long long n = (unsigned long long)j->w * j->h;
@@ -528,11 +674,8 @@ static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cud
   const uint32_t gh = j->sharded ? j->global_h : j->h;
   const unsigned long long offset = j->sharded ? (unsigned long long)j->row_offset * gw : 0ull;
   // plus_plus_init.wgsl:161-167 — seed pixel on the clustered image
-  int64_t sx = j->opts.seed_x >= 0 ? j->opts.seed_x : (int64_t)(int32_t)((float)gw * j->opts.seed_x_frac);
-  int64_t sy = j->opts.seed_y >= 0 ? j->opts.seed_y : (int64_t)(int32_t)((float)gh * j->opts.seed_y_frac);
-  if (sx < 0 || sy < 0 || sx >= (int64_t)gw || sy >= (int64_t)gh)
-    return fail(KMG_ERR_BAD_ARG, "seed pixel (%lld,%lld) outside the %ux%u image", (long long)sx, (long long)sy, gw, gh);
-  const unsigned long long seed = (unsigned long long)sy * gw + (unsigned long long)sx;
+  unsigned long long seed = 0;
+  TRY(resolve_seed(j->opts, gw, gh, &seed));
   const bool seed_local = seed >= offset && seed - offset < n;
   if (!j->dmin) return fail(KMG_ERR_BAD_ARG, "job has no distance plane");
 #if KMG_HAVE_NCCL_HEADER
@@ -836,25 +979,85 @@ extern "C" int kmg_dev_fast_lab_error(kmg_ctx* ctx, float* max_err_out) {
 // k-means on a device-resident RGBA8 image using workspace storage.
 // operations::extract_palette_kmeans (core/src/operations.rs:15-88).
 
+// Seed pixel on the clustered image (plus_plus_init.wgsl:161-167).
+static int resolve_seed(const kmg_opts& o, uint32_t gw, uint32_t gh, unsigned long long* seed) {
+  int64_t sx = o.seed_x >= 0 ? o.seed_x : (int64_t)(int32_t)((float)gw * o.seed_x_frac);
+  int64_t sy = o.seed_y >= 0 ? o.seed_y : (int64_t)(int32_t)((float)gh * o.seed_y_frac);
+  if (sx < 0 || sy < 0 || sx >= (int64_t)gw || sy >= (int64_t)gh)
+    return fail(KMG_ERR_BAD_ARG, "seed pixel (%lld,%lld) outside the %ux%u image", (long long)sx, (long long)sy, gw, gh);
+  *seed = (unsigned long long)sy * gw + (unsigned long long)sx;
+  return KMG_OK;
+}
+
+// The fused path: n_frames images of w x h (back to back in d_rgba), one thread-block cluster
+// each, job blobs blob_stride apart in `blob`.  Leaves centroids, state, table, dither threshold
+// and RGBA8 palette in every blob.  Asynchronous on s.
+static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uint8_t* d_rgba, uint32_t n_frames,
+                                  uint32_t w, uint32_t h, uint32_t iw, uint32_t ih, uint32_t k, int cs, const kmg_opts& o,
+                                  void* blob, size_t blob_stride, kmg_job* job, cudaStream_t s) {
+  unsigned long long seed = 0;
+  TRY(resolve_seed(o, iw, ih, &seed));
+  job->ctx = ctx;
+  job->work = nullptr;
+  job->w = iw;
+  job->h = ih;
+  job->k = k;
+  job->color_space = cs;
+  job->opts = o;
+  job->blob = blob;
+  job_carve(job, blob);
+  SmallParams prm;
+  prm.src = (const uint32_t*)d_rgba;
+  prm.frame_px = (unsigned long long)w * h;
+  prm.sw = w;
+  prm.sh = h;
+  prm.dw = iw;
+  prm.dh = ih;
+  prm.shrink = (iw != w || ih != h) ? 1 : 0;
+  prm.ppc = plan.ppc;
+  prm.seed = (unsigned int)seed;
+  prm.k = k;
+  prm.max_iter = o.max_iter ? o.max_iter : 1;
+  prm.check_every = o.check_every;
+  prm.conv_threshold = o.convergence >= 0.0f ? o.convergence : (cs == KMG_LAB ? 1.0f : 0.01f);  // lib.rs:189-194
+  prm.color_space = cs;
+  prm.want_palette = 1;
+  prm.blob_stride = blob_stride;
+  prm.lut = ctx->d_lut;
+  return launch_small(ctx, plan, prm, job->P, n_frames, s);
+}
+
+// Returns with the job's final state on its way into ws->h_state (read it after the caller's
+// next stream synchronisation).  *prepared: the blob already holds table + palette for the remap.
 static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, uint32_t w, uint32_t h, uint32_t k,
-                            int cs, const kmg_opts& o, kmg_job* job, uint32_t* passes_out) {
+                            int cs, const kmg_opts& o, kmg_job* job, bool* prepared) {
   cudaStream_t s = ws->stream;
-  const uint8_t* img = d_rgba;
   uint32_t iw = w, ih = h;
-  if (o.max_dim != 0 && (w > o.max_dim || h > o.max_dim)) {  // structures.rs:67-74
-    kmg_resized_dims(w, h, o.max_dim, &iw, &ih);
+  const bool shrink = o.max_dim != 0 && (w > o.max_dim || h > o.max_dim);  // structures.rs:67-74
+  if (shrink) kmg_resized_dims(w, h, o.max_dim, &iw, &ih);
+  const size_t n = (size_t)iw * ih;
+  TRY(ws->blob.ensure(job_blob_bytes(k)));
+  SmallPlan plan;
+  if (!(o.flags & KMG_OPT_NO_FUSED_KMEANS) && small_plan(ctx, n, k, 1, &plan)) {
+    job->h_state = ws->h_state;
+    TRY(kmeans_small_on_device(ctx, plan, d_rgba, 1, w, h, iw, ih, k, cs, o, ws->blob.p, 0, job, s));
+    CU(cudaMemcpyAsync(ws->h_state, job->P.st, sizeof(JobState), cudaMemcpyDeviceToHost, s));
+    if (prepared) *prepared = true;
+    return KMG_OK;
+  }
+  const uint8_t* img = d_rgba;
+  if (shrink) {
     TRY(ws->small.ensure((size_t)iw * ih * 4));
     TRY(launch_resize(ctx, d_rgba, w, h, (uint8_t*)ws->small.p, iw, ih, s));
     img = (const uint8_t*)ws->small.p;
   }
-  const size_t n = (size_t)iw * ih;
   TRY(ws->work.ensure(n * 16));
   TRY(ws->dmin.ensure(n * 4));
-  TRY(ws->blob.ensure(job_blob_bytes(k)));
   TRY(launch_convert(ctx, img, n, cs, (float*)ws->work.p, s));
   TRY(job_setup(job, ctx, (const float*)ws->work.p, iw, ih, k, cs, o, ws->blob.p, (float*)ws->dmin.p, ws->h_state, s));
   TRY(job_init_impl(job, nullptr, nullptr, s));
-  TRY(job_run_impl(job, passes_out, s));
+  TRY(job_run_impl(job, nullptr, s));
+  if (prepared) *prepared = false;
   return KMG_OK;
 }
 
@@ -878,9 +1081,10 @@ extern "C" int kmg_kmeans_palette(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w,
   TRY(ws->in.ensure(bytes));
   CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, ws->stream));
   kmg_job job;
-  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, passes_out));
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, nullptr));
   CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, ws->stream));
   CU(cudaStreamSynchronize(ws->stream));
+  if (passes_out) *passes_out = ws->h_state->passes;
   return KMG_OK;
 }
 
@@ -925,11 +1129,13 @@ extern "C" int kmg_reduce(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_
   TRY(ws->out.ensure(bytes));
   CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, s));
   kmg_job job;
-  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, passes_out));
-  TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, h, mode, (uint8_t*)ws->out.p, s));
+  bool prepared = false;
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, &prepared));
+  TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, h, mode, (uint8_t*)ws->out.p, s, prepared));
   CU(cudaMemcpyAsync(out_rgba, ws->out.p, bytes, cudaMemcpyDeviceToHost, s));
   if (centroids_out) CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  if (passes_out) *passes_out = ws->h_state->passes;
   return KMG_OK;
 }
 
@@ -955,30 +1161,70 @@ extern "C" int kmg_resize(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_
 // ------------------------------------------------------------------------------------------------
 // batches of frames (BASELINE config 5)
 
+static size_t batch_blob_stride(uint32_t k) { return (job_blob_bytes(k) + 255) & ~(size_t)255; }
+
+// Clustered size of a w x h frame under opts, and whether the fused kernel can take a batch of them.
+static bool batch_plan(kmg_ctx* ctx, uint32_t w, uint32_t h, uint32_t k, uint32_t n_frames, const kmg_opts& o,
+                       uint32_t* iw, uint32_t* ih, SmallPlan* plan) {
+  *iw = w;
+  *ih = h;
+  if (o.max_dim != 0 && (w > o.max_dim || h > o.max_dim)) kmg_resized_dims(w, h, o.max_dim, iw, ih);
+  if (o.flags & KMG_OPT_NO_FUSED_KMEANS) return false;
+  return small_plan(ctx, (unsigned long long)*iw * *ih, k, n_frames, plan);
+}
+
+// Fused batch on device buffers: ONE cluster launch for the k-means of all frames, ONE remap launch
+// (frames on gridDim.y), strided read-back of centroids / pass counts.  Asynchronous on s.
+static int reduce_batch_fused(kmg_ctx* ctx, const SmallPlan& plan, const uint8_t* d_rgba, uint32_t n_frames, uint32_t w,
+                              uint32_t h, uint32_t iw, uint32_t ih, uint32_t k, int cs, int mode, const kmg_opts& o,
+                              uint8_t* d_out, void* blobs, float* centroids_out, uint32_t* passes_out, cudaStream_t s) {
+  const size_t stride = batch_blob_stride(k);
+  kmg_job job;
+  TRY(kmeans_small_on_device(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, o, blobs, stride, &job, s));
+  TRY(launch_remap(&job, d_rgba, w, h, mode, d_out, s, true, n_frames, stride));
+  if (centroids_out)
+    CU(cudaMemcpy2DAsync(centroids_out, (size_t)k * 16, job.P.cent, stride, (size_t)k * 16, n_frames, cudaMemcpyDeviceToHost, s));
+  if (passes_out)
+    CU(cudaMemcpy2DAsync(passes_out, 4, &job.P.st->passes, stride, 4, n_frames, cudaMemcpyDeviceToHost, s));
+  return KMG_OK;
+}
+
 extern "C" int kmg_dev_reduce_batch(kmg_ctx* ctx, const uint8_t* d_rgba, uint32_t n_frames, uint32_t w, uint32_t h,
                                     uint32_t k, int cs, int mode, const kmg_opts* opts, uint8_t* d_out,
                                     float* centroids_out, uint32_t* passes_out, void* stream) {
   TRY(check_image_args("kmg_dev_reduce_batch", ctx, d_rgba, w, h, k, cs));
   if (!d_out || n_frames == 0) return fail(KMG_ERR_BAD_ARG, "kmg_dev_reduce_batch: bad argument");
   if (mode < KMG_REPLACE || mode > KMG_MELD) return fail(KMG_ERR_BAD_ARG, "kmg_dev_reduce_batch: unknown mode %d", mode);
-  (void)stream;
   CU(cudaSetDevice(ctx->device));
   Workspace* ws = ws_acquire(ctx);
   if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
   WsGuard guard{ctx, ws};
   const kmg_opts o = resolve_opts(opts);
   const size_t frame_bytes = (size_t)w * h * 4;
+  uint32_t iw, ih;
+  SmallPlan plan;
+  if (batch_plan(ctx, w, h, k, n_frames, o, &iw, &ih, &plan)) {
+    // the frames were produced on the caller's stream: stay on it
+    cudaStream_t s = pick_stream(ctx, stream);
+    TRY(ws->blob.ensure((size_t)n_frames * batch_blob_stride(k)));
+    TRY(reduce_batch_fused(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, mode, o, d_out, ws->blob.p, centroids_out,
+                           passes_out, s));
+    CU(cudaStreamSynchronize(s));
+    return KMG_OK;
+  }
+  // frame by frame through the staged path (k > 32, or frames too large for a cluster)
+  CU(cudaStreamSynchronize(pick_stream(ctx, stream)));
   for (uint32_t f = 0; f < n_frames; ++f) {
     kmg_job job;
-    uint32_t passes = 0;
+    bool prepared = false;
     const uint8_t* in = d_rgba + (size_t)f * frame_bytes;
-    TRY(kmeans_on_device(ctx, ws, in, w, h, k, cs, o, &job, &passes));
-    TRY(launch_remap(&job, in, w, h, mode, d_out + (size_t)f * frame_bytes, ws->stream));
+    TRY(kmeans_on_device(ctx, ws, in, w, h, k, cs, o, &job, &prepared));
+    TRY(launch_remap(&job, in, w, h, mode, d_out + (size_t)f * frame_bytes, ws->stream, prepared));
     if (centroids_out)
       CU(cudaMemcpyAsync(centroids_out + (size_t)f * k * 4, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, ws->stream));
-    if (passes_out) passes_out[f] = passes;
     // the workspace blob is reused by the next frame: drain before overwriting it
     CU(cudaStreamSynchronize(ws->stream));
+    if (passes_out) passes_out[f] = ws->h_state->passes;
   }
   return KMG_OK;
 }
@@ -988,12 +1234,57 @@ extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_fr
                                 float* centroids_out, uint32_t* passes_out) {
   TRY(check_image_args("kmg_reduce_batch", ctx, rgba, w, h, k, cs));
   if (!out_rgba || n_frames == 0) return fail(KMG_ERR_BAD_ARG, "kmg_reduce_batch: bad argument");
-  for (uint32_t f = 0; f < n_frames; ++f) {
-    const size_t off = (size_t)f * w * h * 4;
-    TRY(kmg_reduce(ctx, rgba + off, w, h, k, cs, mode, opts, out_rgba + off,
-                   centroids_out ? centroids_out + (size_t)f * k * 4 : nullptr, passes_out ? passes_out + f : nullptr));
+  if (mode < KMG_REPLACE || mode > KMG_MELD) return fail(KMG_ERR_BAD_ARG, "kmg_reduce_batch: unknown mode %d", mode);
+  CU(cudaSetDevice(ctx->device));
+  const kmg_opts o = resolve_opts(opts);
+  const size_t frame_bytes = (size_t)w * h * 4;
+  uint32_t iw, ih;
+  SmallPlan plan;
+  if (n_frames == 1 || !batch_plan(ctx, w, h, k, n_frames, o, &iw, &ih, &plan)) {
+    for (uint32_t f = 0; f < n_frames; ++f) {
+      const size_t off = (size_t)f * frame_bytes;
+      TRY(kmg_reduce(ctx, rgba + off, w, h, k, cs, mode, opts, out_rgba + off,
+                     centroids_out ? centroids_out + (size_t)f * k * 4 : nullptr, passes_out ? passes_out + f : nullptr));
+    }
+    return KMG_OK;
   }
-  return KMG_OK;
+  // Chunks of frames flow through up to three workspaces (stream + buffers each): the upload of
+  // chunk i+1 and the read-back of chunk i-1 overlap the kernels of chunk i.  Overlap needs the
+  // caller's buffers to be page-locked; pageable buffers still work, the copies then serialise.
+  const uint32_t chunk = (uint32_t)std::min<size_t>(n_frames, std::max<size_t>(16, ((size_t)128 << 20) / frame_bytes));
+  const uint32_t n_chunks = (n_frames + chunk - 1) / chunk;
+  const uint32_t n_ws = std::min<uint32_t>(3, n_chunks);
+  Workspace* wss[3] = {nullptr, nullptr, nullptr};
+  int rc = KMG_OK;
+  for (uint32_t i = 0; i < n_ws && rc == KMG_OK; ++i) {
+    wss[i] = ws_acquire(ctx);
+    if (!wss[i]) rc = fail(KMG_ERR_CUDA, "could not create a workspace");
+  }
+  auto run = [&]() -> int {
+    const size_t stride = batch_blob_stride(k);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      Workspace* ws = wss[c % n_ws];
+      const uint32_t f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+      TRY(ws->in.ensure((size_t)nf * frame_bytes));
+      TRY(ws->out.ensure((size_t)nf * frame_bytes));
+      TRY(ws->blob.ensure((size_t)nf * stride));
+      cudaStream_t s = ws->stream;
+      CU(cudaMemcpyAsync(ws->in.p, rgba + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, s));
+      TRY(reduce_batch_fused(ctx, plan, (const uint8_t*)ws->in.p, nf, w, h, iw, ih, k, cs, mode, o, (uint8_t*)ws->out.p,
+                             ws->blob.p, centroids_out ? centroids_out + (size_t)f0 * k * 4 : nullptr,
+                             passes_out ? passes_out + f0 : nullptr, s));
+      CU(cudaMemcpyAsync(out_rgba + (size_t)f0 * frame_bytes, ws->out.p, (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    for (uint32_t i = 0; i < n_ws; ++i) CU(cudaStreamSynchronize(wss[i]->stream));
+    return KMG_OK;
+  };
+  if (rc == KMG_OK) rc = run();
+  for (uint32_t i = 0; i < 3; ++i)
+    if (wss[i]) {
+      if (rc != KMG_OK) cudaStreamSynchronize(wss[i]->stream);
+      ws_release(ctx, wss[i]);
+    }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

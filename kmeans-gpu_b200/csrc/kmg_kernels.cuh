@@ -58,6 +58,20 @@ struct JobPtrs {
 
 __host__ __device__ inline unsigned int pad32(unsigned int k) { return (k + 31u) & ~31u; }
 
+// The job blob of frame f in a batch: every pointer shifted by f * blob_stride bytes.
+__device__ __forceinline__ JobPtrs job_at(JobPtrs J, size_t off) {
+  JobPtrs R;
+  R.st = reinterpret_cast<JobState*>(reinterpret_cast<unsigned char*>(J.st) + off);
+  R.cent = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(J.cent) + off);
+  R.tab = reinterpret_cast<CentRec*>(reinterpret_cast<unsigned char*>(J.tab) + off);
+  R.acc = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(J.acc) + off);
+  R.last = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(J.last) + off);
+  R.keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(J.keys) + off);
+  R.pal = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(J.pal) + off);
+  R.acc_copies = J.acc_copies;
+  return R;
+}
+
 // Shared-memory copy of the table: every chunk of 8 records (192 B) is followed by 16 B of padding,
 // so chunk bases advance by an odd number of 16-byte bank groups and lanes that read *different*
 // chunks (winning-chunk rescan, cooperative exact path) do not all collide on the same banks.
@@ -364,7 +378,6 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
   }
   for (unsigned int c = 0; c < kp; c += 8) {
     fast::f32x2 s2[8][H];
-#pragma unroll
     float f[48];
     load_chunk(rec_at(tab, c), f);
 #pragma unroll
@@ -492,39 +505,45 @@ __global__ void __launch_bounds__(256) k_convert(const uint32_t* __restrict__ rg
 }
 
 // ------------------------------------------------------------------------------------------------
-// K15: bilinear shrink, exact restatement (see oracle resize_image).
+// K15: bilinear shrink, exact restatement (see oracle resize_image).  One destination pixel p of
+// the dw x dh image sampled from the sw x sh source: resize.wgsl:5-19 with a linear / clamp-to-edge
+// sampler at (gx/dw, gy/dh), unorm8 store.
+__device__ __forceinline__ uint32_t resize_pixel(const uint32_t* __restrict__ src, unsigned int sw, unsigned int sh,
+                                                 unsigned int dw, unsigned int dh, unsigned long long p) {
+  unsigned int gx = (unsigned int)(p % dw), gy = (unsigned int)(p / dw);
+  float py = fsub(fmul(fdiv((float)gy, (float)dh), (float)sh), 0.5f);
+  float px = fsub(fmul(fdiv((float)gx, (float)dw), (float)sw), 0.5f);
+  float fy0 = floorf(py), fx0 = floorf(px);
+  float fy = fsub(py, fy0), fx = fsub(px, fx0);
+  long long y0 = (long long)fy0, x0 = (long long)fx0;
+  long long y1 = y0 + 1, x1 = x0 + 1;
+  y0 = min(max(y0, 0ll), (long long)sh - 1);
+  y1 = min(max(y1, 0ll), (long long)sh - 1);
+  x0 = min(max(x0, 0ll), (long long)sw - 1);
+  x1 = min(max(x1, 0ll), (long long)sw - 1);
+  uint32_t p00 = __ldg(src + (size_t)y0 * sw + x0), p10 = __ldg(src + (size_t)y0 * sw + x1);
+  uint32_t p01 = __ldg(src + (size_t)y1 * sw + x0), p11 = __ldg(src + (size_t)y1 * sw + x1);
+  float wx0 = fsub(1.0f, fx), wy0 = fsub(1.0f, fy);
+  uint32_t o = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float c00 = fdiv((float)((p00 >> (8 * c)) & 255u), 255.0f);
+    float c10 = fdiv((float)((p10 >> (8 * c)) & 255u), 255.0f);
+    float c01 = fdiv((float)((p01 >> (8 * c)) & 255u), 255.0f);
+    float c11 = fdiv((float)((p11 >> (8 * c)) & 255u), 255.0f);
+    float top = fadd(fmul(c00, wx0), fmul(c10, fx));
+    float bot = fadd(fmul(c01, wx0), fmul(c11, fx));
+    o |= ex::unorm8(fadd(fmul(top, wy0), fmul(bot, fy))) << (8 * c);
+  }
+  return o;
+}
+
 __global__ void __launch_bounds__(256) k_resize(const uint32_t* __restrict__ src, unsigned int sw, unsigned int sh,
                                                 uint32_t* __restrict__ dst, unsigned int dw, unsigned int dh) {
   const unsigned long long n = (unsigned long long)dw * dh;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    unsigned int gx = (unsigned int)(p % dw), gy = (unsigned int)(p / dw);
-    float py = fsub(fmul(fdiv((float)gy, (float)dh), (float)sh), 0.5f);
-    float px = fsub(fmul(fdiv((float)gx, (float)dw), (float)sw), 0.5f);
-    float fy0 = floorf(py), fx0 = floorf(px);
-    float fy = fsub(py, fy0), fx = fsub(px, fx0);
-    long long y0 = (long long)fy0, x0 = (long long)fx0;
-    long long y1 = y0 + 1, x1 = x0 + 1;
-    y0 = min(max(y0, 0ll), (long long)sh - 1);
-    y1 = min(max(y1, 0ll), (long long)sh - 1);
-    x0 = min(max(x0, 0ll), (long long)sw - 1);
-    x1 = min(max(x1, 0ll), (long long)sw - 1);
-    uint32_t p00 = __ldg(src + (size_t)y0 * sw + x0), p10 = __ldg(src + (size_t)y0 * sw + x1);
-    uint32_t p01 = __ldg(src + (size_t)y1 * sw + x0), p11 = __ldg(src + (size_t)y1 * sw + x1);
-    float wx0 = fsub(1.0f, fx), wy0 = fsub(1.0f, fy);
-    uint32_t o = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float c00 = fdiv((float)((p00 >> (8 * c)) & 255u), 255.0f);
-      float c10 = fdiv((float)((p10 >> (8 * c)) & 255u), 255.0f);
-      float c01 = fdiv((float)((p01 >> (8 * c)) & 255u), 255.0f);
-      float c11 = fdiv((float)((p11 >> (8 * c)) & 255u), 255.0f);
-      float top = fadd(fmul(c00, wx0), fmul(c10, fx));
-      float bot = fadd(fmul(c01, wx0), fmul(c11, fx));
-      o |= ex::unorm8(fadd(fmul(top, wy0), fmul(bot, fy))) << (8 * c);
-    }
-    dst[p] = o;
-  }
+  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    dst[p] = resize_pixel(src, sw, sh, dw, dh, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -901,10 +920,15 @@ __device__ __noinline__ float4 remap_exact_pixel(uint32_t v, const float* __rest
 }
 
 template <int MODE, int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t* __restrict__ rgba, unsigned int w,
+__global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t* __restrict__ rgba, unsigned int w,
                                                    unsigned long long n, int color_space,
-                                                   const float* __restrict__ lut_g, uint32_t* __restrict__ out) {
+                                                   const float* __restrict__ lut_g, uint32_t* __restrict__ out,
+                                                   size_t blob_stride) {
   // KT > 0: compile-time table length; KT == 0: runtime length.  Table + palette in dynamic smem.
+  // blockIdx.y = frame of a batch (frames of n pixels back to back, job blobs blob_stride apart).
+  const JobPtrs J = job_at(J0, (size_t)blockIdx.y * blob_stride);
+  rgba += (size_t)blockIdx.y * n;
+  out += (size_t)blockIdx.y * n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CentRec* s_tab = reinterpret_cast<CentRec*>(smem_raw);
   __shared__ float lut[256];
@@ -1022,9 +1046,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J, const uint32_t*
 }
 
 // Meld (K14, mix_colors.wgsl:29-48,85-90,115-136): continuous output, evaluated exactly per pixel.
-__global__ void __launch_bounds__(256) k_remap_meld(JobPtrs J, const uint32_t* __restrict__ rgba,
+__global__ void __launch_bounds__(256) k_remap_meld(JobPtrs J0, const uint32_t* __restrict__ rgba,
                                                     unsigned long long n, int color_space,
-                                                    const float* __restrict__ lut_g, uint32_t* __restrict__ out) {
+                                                    const float* __restrict__ lut_g, uint32_t* __restrict__ out,
+                                                    size_t blob_stride) {
+  const JobPtrs J = job_at(J0, (size_t)blockIdx.y * blob_stride);
+  rgba += (size_t)blockIdx.y * n;
+  out += (size_t)blockIdx.y * n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_cent = reinterpret_cast<float4*>(smem_raw);
   __shared__ float lut[256];

@@ -74,10 +74,12 @@ class Opts:
     seed_y_frac: float = 0.93359375
     seed_x: int = -1
     seed_y: int = -1
+    fused_kmeans: bool = True  # False: KMG_OPT_NO_FUSED_KMEANS (stage-by-stage launches; same results)
 
     def to_c(self) -> KmgOpts:
         return KmgOpts(C.sizeof(KmgOpts), self.max_dim, self.max_iter, self.check_every, self.convergence,
-                       self.seed_x_frac, self.seed_y_frac, self.seed_x, self.seed_y)
+                       self.seed_x_frac, self.seed_y_frac, self.seed_x, self.seed_y,
+                       0 if self.fused_kmeans else _native.KMG_OPT_NO_FUSED_KMEANS)
 
 
 class Image:

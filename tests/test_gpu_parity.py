@@ -338,6 +338,88 @@ def test_reduce_batch_matches_single(proc, K, oracle):
         assert np.array_equal(out[f], want)
 
 
+# ---- fused (one thread-block cluster per image) vs staged k-means ---------------------------------
+
+@pytest.mark.parametrize("w,h,k,cs", [(256, 171, 8, 0), (256, 144, 16, 0), (256, 256, 16, 0), (256, 256, 32, 0),
+                                      (200, 256, 3, 0), (97, 61, 8, 0), (33, 7, 5, 0), (5, 3, 2, 0), (1, 1, 1, 0),
+                                      (3, 1, 4, 0), (256, 200, 17, 0), (128, 128, 24, 1), (255, 255, 9, 1),
+                                      (640, 360, 12, 0), (1000, 30, 6, 0)])
+def test_fused_kmeans_matches_staged_and_oracle(proc, K, oracle, w, h, k, cs):
+    """kmg_small.cuh against the stage-by-stage launches and the oracle: centroids, pass counts and
+    the remapped image bit for bit (clusters of 16 CTAs for single images)."""
+    img = oracle.synth(w * h, seed=11 + k, blobs=max(2, 2 * k)).reshape(h, w, 4)
+    mode = K.ReduceMode.Dither if k % 2 == 0 else K.ReduceMode.Replace
+    space = K.ColorSpace(cs)
+    out_f, cent_f, passes_f = proc.reduce(k, img, reduce_mode=mode, color_space=space, return_details=True)
+    out_s, cent_s, passes_s = proc.reduce(k, img, reduce_mode=mode, color_space=space, return_details=True,
+                                          opts=K.Opts(fused_kmeans=False))
+    assert passes_f == passes_s
+    assert np.array_equal(bits(cent_f), bits(cent_s))
+    assert np.array_equal(out_f.rgba, out_s.rgba)
+    ocent, opasses = oracle.kmeans(img, k, cs, opts=oracle.default_opts(sum_mode=1))
+    assert passes_f == opasses
+    assert np.array_equal(bits(cent_f), bits(ocent))
+
+
+def test_fused_kmeans_options_and_ties(proc, K, oracle):
+    """Explicit seed, other iteration limits, no shrink; an image of two flat colours (every
+    init distance tied, empty clusters, duplicate centroids)."""
+    img = oracle.synth(240 * 100, seed=2, blobs=16).reshape(100, 240, 4)
+    for kw in (dict(max_dim=0, max_iter=20, check_every=4, seed_x=7, seed_y=9), dict(max_dim=64, max_iter=3),
+               dict(max_iter=1), dict(check_every=0, max_iter=11), dict(convergence=0.05)):
+        cent, passes = proc.kmeans_centroids(8, img, opts=K.Opts(**kw))
+        ocent, opasses = oracle.kmeans(img, 8, opts=oracle.default_opts(sum_mode=1, **kw))
+        assert passes == opasses, kw
+        assert np.array_equal(bits(cent), bits(ocent)), kw
+    flat = np.zeros((64, 80, 4), np.uint8)
+    flat[..., 3] = 255
+    flat[:, 40:, :3] = (200, 30, 90)
+    for k in (1, 2, 5, 16):
+        out, cent, passes = proc.reduce(k, flat, return_details=True)
+        want, ocent, opasses = oracle.reduce(flat, k, "replace")
+        assert passes == opasses
+        assert np.array_equal(bits(cent), bits(ocent))
+        assert np.array_equal(out.rgba, want)
+
+
+@pytest.mark.parametrize("k,mode", [(16, "dither"), (8, "replace"), (20, "dither"), (40, "replace")])
+def test_reduce_batch_device_and_host_pipeline(proc, D, K, oracle, torch, k, mode):
+    """BASELINE config 5 in miniature: frames resident in HBM (one cluster launch + one remap launch
+    for the whole batch) and the chunked host pipeline, against per-frame reduce and the oracle."""
+    n, w, h = 37, 480, 270
+    frames = np.stack([oracle.synth(w * h, seed=3, blobs=32, frame=f).reshape(h, w, 4) for f in range(n)])
+    rm = K.ReduceMode.Dither if mode == "dither" else K.ReduceMode.Replace
+    dev_out, dev_cent, dev_passes = D.reduce_batch(proc, dev_rgba(torch, frames), k, rm)
+    host_out, host_cent, host_passes = proc.reduce_batch(k, frames, rm)
+    assert np.array_equal(dev_out.cpu().numpy(), host_out)
+    assert np.array_equal(bits(dev_cent), bits(host_cent)) and np.array_equal(dev_passes, host_passes)
+    for f in (0, 1, 17, n - 1):
+        single, cent, passes = proc.reduce(k, frames[f], reduce_mode=rm, return_details=True)
+        assert passes == host_passes[f]
+        assert np.array_equal(bits(cent), bits(host_cent[f]))
+        assert np.array_equal(single.rgba, host_out[f])
+    want, ocent, opasses = oracle.reduce(frames[5], k, mode)
+    assert opasses == host_passes[5]
+    assert np.array_equal(bits(ocent), bits(host_cent[5]))
+    assert np.array_equal(want, host_out[5])
+
+
+def test_reduce_batch_many_chunks(proc, K, oracle):
+    """More frames than one pipeline chunk holds (chunks of >= 16 frames through three workspaces)."""
+    n, w, h = 70, 1920, 1080
+    base = oracle.synth(w * h, seed=3, blobs=32, frame=0).reshape(h, w, 4)
+    frames = np.empty((n, h, w, 4), np.uint8)
+    for f in range(n):
+        frames[f] = np.roll(base, 97 * f, axis=1)
+        frames[f, :8, :8, :3] = f  # make every frame distinct
+    out, cent, passes = proc.reduce_batch(16, frames, K.ReduceMode.Dither)
+    for f in (0, 15, 16, 33, n - 1):
+        single, c1, p1 = proc.reduce(16, frames[f], reduce_mode=K.ReduceMode.Dither, return_details=True)
+        assert p1 == passes[f]
+        assert np.array_equal(bits(c1), bits(cent[f]))
+        assert np.array_equal(single.rgba, out[f])
+
+
 # ---- boundary behaviour --------------------------------------------------------------------------
 
 def test_errors(proc, K, tokyo):
