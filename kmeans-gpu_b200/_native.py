@@ -9,7 +9,10 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libkmeans_gpu.so"
+import os
+
+# KMG_LIB_PATH: development override (e.g. the `make TRACE=1` build); the product is lib/libkmeans_gpu.so
+LIB_PATH = Path(os.environ["KMG_LIB_PATH"]) if os.environ.get("KMG_LIB_PATH") else PKG / "lib" / "libkmeans_gpu.so"
 
 KMG_OK = 0
 STATUS_NAMES = {1: "BAD_ARG", 2: "CUDA", 3: "OOM", 4: "NCCL", 5: "UNSUPPORTED"}

@@ -37,9 +37,9 @@ using namespace kmg;
 #define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
 static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
 // Whole-k-means-in-one-launch variants (kmg_small.cuh): <table/accumulator capacity, threads>
-#define SMALL8 k_kmeans_small<8, 256>
-#define SMALL16 k_kmeans_small<16, 256>
-#define SMALL32 k_kmeans_small<32, 128>
+#define SMALL8 k_kmeans_small<8, 512>
+#define SMALL16 k_kmeans_small<16, 512>
+#define SMALL32 k_kmeans_small<32, 256>
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -275,7 +275,7 @@ static inline int grid_for(kmg_ctx* ctx, unsigned long long items, int per_block
 // fused small-image k-means (kmg_small.cuh): capability probe, plan, launch
 
 struct SmallPlan {
-  int variant = -1;          // 0: <8,256>, 1: <16,256>, 2: <32,128>
+  int variant = -1;          // 0: <8,512>, 1: <16,512>, 2: <32,256>
   unsigned int kcap = 0, threads = 0, csize = 0, ppc = 0;
   size_t smem = 0;
 };
@@ -283,7 +283,7 @@ static const void* small_fn(int variant) {
   return variant == 0 ? (const void*)SMALL8 : variant == 1 ? (const void*)SMALL16 : (const void*)SMALL32;
 }
 static const unsigned int SMALL_KCAP[3] = {8, 16, 32};
-static const unsigned int SMALL_THREADS[3] = {256, 256, 128};
+static const unsigned int SMALL_THREADS[3] = {512, 512, 256};
 
 static void small_probe(kmg_ctx* ctx, const cudaDeviceProp& prop) {
   for (int v = 0; v < 3; ++v) {
@@ -1344,3 +1344,12 @@ extern "C" int kmg_comm_destroy(kmg_ctx* ctx) {
   return KMG_OK;
 #endif
 }
+
+#ifdef KMG_TRACE
+// Development aid (make TRACE=1): phase timestamps of the last k_kmeans_small launch, 16 x 512 clock64 values.
+extern "C" int kmg_debug_small_trace(uint64_t* out) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out, g_small_trace, sizeof(unsigned long long) * SMALL_MAX_CLUSTER * 512));
+  return KMG_OK;
+}
+#endif

@@ -53,9 +53,32 @@ __device__ __forceinline__ float srgb_decode100(uint32_t v) {
   float r = (c > 0.04045f) ? pow_f32(fdiv(fadd(c, 0.055f), 1.055f), 2.4f) : fdiv(c, 12.92f);
   return fmul(r, 100.0f);
 }
+// pow_f32(t, 1.0f / 3.0f) for 2^-10 < t < 2^4 without the ~200 FP64 instructions of pow():
+// one Newton step of the cube root in double from a MUFU seed (relative error <= ~3e-13), times
+// t^(e - 1/3) for the f32 exponent e = 0.3333333432674408 (= 1 + (e - 1/3) ln t to 1e-15), rounded
+// to f32.  Ziv's test: when the double lies within 2e-12 (relative) of an f32 rounding boundary,
+// or the result is a power of two, the full pow() decides — so the value returned is always the
+// one pow_f32 returns (checked over all 2^24 colours by test_convert_lab_all_16m_colours).
+__device__ __noinline__ float pow_third_slow(float t) { return pow_f32(t, 1.0f / 3.0f); }
+__device__ __forceinline__ float pow_third(float t) {
+  float lg, y0, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(lg * 0.33333334f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(3.0f * y0 * y0));
+  const double y0d = (double)y0;
+  const double res = fma(y0d * y0d, y0d, -(double)t);
+  const double y1 = fma(-res, (double)r, y0d);
+  const double yd = y1 * fma(6.885803302144935e-9, (double)lg, 1.0);  // (e - 1/3) * ln 2 * log2 t
+  const float f = __double2float_rn(yd);
+  const double h = (double)__int_as_float((__float_as_int(f) & 0x7f800000) - (24 << 23));  // half an ulp of f
+  const double gap = fabs(fabs(yd - (double)f) - h);
+  if (gap < 2.0e-12 * yd || (__float_as_int(f) & 0x007fffff) == 0) return pow_third_slow(t);
+  return f;
+}
+
 // core/shaders/converters/rgb_to_lab.wgsl:39-64
 __device__ __forceinline__ float lab_f(float t) {
-  if (t > 0.008856f) return pow_f32(t, 1.0f / 3.0f);
+  if (t > 0.008856f) return pow_third(t);
   return fadd(fmul(7.787f, t), 16.0f / 116.0f);
 }
 // r,g,b already decoded and scaled by 100 (table lookup).

@@ -29,6 +29,20 @@ namespace cg = cooperative_groups;
 
 constexpr unsigned int SMALL_MAX_CLUSTER = 16;
 
+// Development aid (make TRACE=1): warp 0 / lane 0 of every CTA of frame 0 records clock64() at the
+// phase boundaries.  Not compiled into the product library.
+#ifdef KMG_TRACE
+__device__ unsigned long long g_small_trace[SMALL_MAX_CLUSTER][512];
+#define KMG_TRACE_DECL unsigned int trace_n = 0
+#define KMG_TRACE_MARK()                                                              \
+  do {                                                                                \
+    if (tid == 0 && frame == 0 && trace_n < 512) g_small_trace[rank][trace_n++] = clock64(); \
+  } while (0)
+#else
+#define KMG_TRACE_DECL
+#define KMG_TRACE_MARK() do {} while (0)
+#endif
+
 struct SmallParams {
   const uint32_t* src;           // frame 0, full size
   unsigned long long frame_px;   // pixels per source frame (stride between frames)
@@ -57,10 +71,11 @@ __host__ __device__ inline size_t small_smem_bytes(unsigned int ppc, unsigned in
 template <int KCAP, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, JobPtrs J0) {
   static_assert(KCAP == 8 || KCAP == 16 || KCAP == 32, "table capacity");
-  static_assert(THREADS % KCAP == 0 && THREADS / KCAP <= 32, "fold groups live inside a warp");
-  constexpr int P = KCAP == 16 ? 2 : 4;
-  constexpr int G = THREADS / KCAP;  // threads that fold one cluster's slots
+  static_assert(THREADS % KCAP == 0, "fold groups");
+  constexpr int P = KCAP == 8 ? 4 : 2;
+  constexpr int G = THREADS / KCAP < 32 ? THREADS / KCAP : 32;  // lanes that fold one cluster's slots
   constexpr int NW = THREADS / 32;
+  constexpr int TAB_BYTES = (KCAP / 8) * CHUNK_BYTES;
 
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int csize = cluster.num_blocks();
@@ -77,15 +92,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   float* s_dmin = reinterpret_cast<float*>(smem_raw + (size_t)ppc * 16);
   int4* s_acc = reinterpret_cast<int4*>(smem_raw + (size_t)ppc * 20);
   long long* s_x = reinterpret_cast<long long*>(smem_raw + (size_t)ppc * 20 + (size_t)KCAP * THREADS * 16);
-  __shared__ __align__(16) unsigned char s_tab_raw[(KCAP / 8) * CHUNK_BYTES];
-  __shared__ float4 s_cent[KCAP];
+  // every warp keeps its own copy of the centroids and of the search table, so the finalisation
+  // of a pass needs no block-wide barrier (all warps compute identical values)
+  __shared__ __align__(16) unsigned char s_tab_raw[NW][TAB_BYTES];
+  __shared__ float4 s_cent[NW][KCAP];
   __shared__ float s_lut[256];
   __shared__ unsigned long long s_keys[2][SMALL_MAX_CLUSTER];
   __shared__ unsigned long long s_red[NW];
-  __shared__ long long s_last[KCAP * 4];
-  __shared__ float s_bounds[2];
   __shared__ unsigned int s_slow;
-  CentRec* s_tab = reinterpret_cast<CentRec*>(s_tab_raw);
+  CentRec* s_tab = reinterpret_cast<CentRec*>(s_tab_raw[warp]);
+  float4* my_cent = s_cent[warp];
 
   const JobPtrs J = job_at(J0, (size_t)frame * prm.blob_stride);
   const uint32_t* src = prm.src + (size_t)frame * prm.frame_px;
@@ -93,16 +109,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   const unsigned int first = rank * ppc;
   const unsigned int n_local = first < N ? min(ppc, N - first) : 0u;
 
+  KMG_TRACE_DECL;
+  KMG_TRACE_MARK();  // 0: start
   // ---- shrink + convert into the local slice of the work plane --------------------------------
   for (unsigned int c = tid; c < 256; c += THREADS) s_lut[c] = prm.lut[c];
-  __syncthreads();
-  for (unsigned int i = tid; i < n_local; i += THREADS) {
-    const unsigned int g = first + i;
-    const uint32_t v = prm.shrink ? resize_pixel(src, prm.sw, prm.sh, prm.dw, prm.dh, g) : __ldg(src + g);
-    s_work[i] = prm.color_space == 0 ? ex::lin100_to_lab(s_lut[v & 255u], s_lut[(v >> 8) & 255u], s_lut[(v >> 16) & 255u])
-                                     : ex::rgb8_to_rgbf(v);
+  if (tid == 0) s_slow = 0;
+  {
+    // pass 1: RGBA8 of the clustered image (the loads of several pixels in flight), parked in the
+    // distance plane; pass 2: exact conversion (FP64 pow) out of shared memory
+    uint32_t* s_px = reinterpret_cast<uint32_t*>(s_dmin);
+#pragma unroll 4
+    for (unsigned int i = tid; i < n_local; i += THREADS)
+      s_px[i] = prm.shrink ? resize_pixel(src, prm.sw, prm.sh, prm.dw, prm.dh, first + i) : __ldg(src + first + i);
+    __syncthreads();
+    KMG_TRACE_MARK();  // 1: resized
+    for (unsigned int i = tid; i < n_local; i += THREADS) {
+      const uint32_t v = s_px[i];
+      s_work[i] = prm.color_space == 0
+                      ? ex::lin100_to_lab(s_lut[v & 255u], s_lut[(v >> 8) & 255u], s_lut[(v >> 16) & 255u])
+                      : ex::rgb8_to_rgbf(v);
+    }
   }
+#pragma unroll 4
+  for (int q = 0; q < KCAP; ++q) s_acc[q * THREADS + tid] = make_int4(0, 0, 0, 0);
+  KMG_TRACE_MARK();  // 2: converted
   cluster.sync();
+  KMG_TRACE_MARK();  // 3: cluster sync
 
   // ---- farthest-point init (plus_plus_init.wgsl, kmeans++_calc_diff.wgsl) ----------------------
   auto pixel_colour = [&](unsigned int g) -> float4 {  // any pixel of the image, through DSMEM
@@ -112,10 +144,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
     return v;
   };
   float4 c = pixel_colour(prm.seed);
-  if (tid == 0) {
-    s_cent[0] = c;
-    if (rank == 0) J.keys[0] = 0ull;
-  }
+  if (lane == 0) my_cent[0] = c;
+  if (tid == 0 && rank == 0) J.keys[0] = 0ull;
   for (unsigned int j = 1; j < k; ++j) {
     const float cc = ex::chroma(c.y, c.z);
     unsigned long long best = 0ull;
@@ -129,72 +159,68 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
     }
     best = warp_max_u64(best);
     if (lane == 0) s_red[warp] = best;
+    KMG_TRACE_MARK();  // init a: scanned
     __syncthreads();
+    KMG_TRACE_MARK();  // init b: block barrier
     if (tid < csize) {  // thread r hands this CTA's maximum to rank r
       unsigned long long b = s_red[0];
 #pragma unroll
       for (int w = 1; w < NW; ++w) b = s_red[w] > b ? s_red[w] : b;
       *cluster.map_shared_rank(&s_keys[j & 1u][rank], tid) = b;
     }
+    KMG_TRACE_MARK();  // init c: sent
     cluster.sync();
+    KMG_TRACE_MARK();  // init d: cluster barrier
     unsigned long long gk = 0ull;
     for (unsigned int r = 0; r < csize; ++r) gk = s_keys[j & 1u][r] > gk ? s_keys[j & 1u][r] : gk;
     c = pixel_colour((unsigned int)key_to_pixel(gk));
-    if (tid == 0) {
-      s_cent[j] = c;
-      if (rank == 0) J.keys[j] = gk;
-    }
+    if (lane == 0) my_cent[j] = c;
+    if (tid == 0 && rank == 0) J.keys[j] = gk;
+    KMG_TRACE_MARK();  // init e: colour fetched
   }
-  __syncthreads();
+  __syncwarp();
 
   // ---- Lloyd loop --------------------------------------------------------------------------------
   unsigned int it = 0, conv = 0;
   unsigned long long slow_total = 0;
+  long long last[4] = {0, 0, 0, 0};  // lane c: reduced sums of cluster c in the last pass
   bool done = false;
   const unsigned int tiles = (ppc + THREADS * P - 1) / (THREADS * P);
-  while (!done) {
-    // table of the current centroids (one warp; KCAP <= 32 entries)
-    if (warp == 0) {
-      float lmax = 0.0f, cmax = 0.0f;
-      if (lane < KCAP) {
-        CentRec r;
-        if (lane < k) {
-          const float4 v = s_cent[lane];
-          const float c2 = ex::chroma(v.y, v.z);
-          bool dup = false;
-          for (unsigned int i = 0; i < lane; ++i) {
-            const float4 u = s_cent[i];
-            dup |= (u.x == v.x && u.y == v.y && u.z == v.z);
-          }
-          r.q[0] = dup ? MASKED : 0.5f * (v.x * v.x);
-          r.q[1] = -v.x;
-          r.q[2] = 0.5f * (c2 * c2);
-          r.q[3] = c2;
-          r.q[4] = -v.y;
-          r.q[5] = -v.z;
-          lmax = fabsf(v.x);
-          cmax = c2;
-        } else {
-          r.q[0] = MASKED;
-          r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
+  while (true) {
+    // this warp's table of the current centroids (KCAP <= 32 entries, one lane each)
+    float lmax = 0.0f, cmax = 0.0f;
+    if (lane < KCAP) {
+      CentRec r;
+      if (lane < k) {
+        const float4 v = my_cent[lane];
+        const float c2 = ex::chroma(v.y, v.z);
+        bool dup = false;
+        for (unsigned int i = 0; i < lane; ++i) {
+          const float4 u = my_cent[i];
+          dup |= (u.x == v.x && u.y == v.y && u.z == v.z);
         }
-        *const_cast<CentRec*>(rec_at(s_tab, lane)) = r;
+        r.q[0] = dup ? MASKED : 0.5f * (v.x * v.x);
+        r.q[1] = -v.x;
+        r.q[2] = 0.5f * (c2 * c2);
+        r.q[3] = c2;
+        r.q[4] = -v.y;
+        r.q[5] = -v.z;
+        lmax = fabsf(v.x);
+        cmax = c2;
+      } else {
+        r.q[0] = MASKED;
+        r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-      }
-      if (lane == 0) {
-        s_bounds[0] = lmax;
-        s_bounds[1] = cmax;
-        s_slow = 0;
-      }
+      *const_cast<CentRec*>(rec_at(s_tab, lane)) = r;
     }
-#pragma unroll 4
-    for (int q = 0; q < KCAP; ++q) s_acc[q * THREADS + tid] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-    const float lmax = s_bounds[0], cmax = s_bounds[1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+      cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    }
+    __syncwarp();
+    KMG_TRACE_MARK();  // pass a: table
+    if (done) break;  // the table of the final centroids is not needed (build_table below redoes it in HBM)
 
     // assignment + thread-private accumulation over the local slice
     unsigned int slow = 0;
@@ -236,18 +262,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
         }
       }
     }
-    if (slow) atomicAdd(&s_slow, slow);
+    if (__any_sync(0xffffffffu, slow != 0)) {
+      slow = __reduce_add_sync(0xffffffffu, slow);
+      if (lane == 0) atomicAdd(&s_slow, slow);
+    }
+    KMG_TRACE_MARK();  // pass b: assigned
     __syncthreads();
+    KMG_TRACE_MARK();  // pass c: block barrier
 
-    // block fold: G consecutive lanes own one cluster's THREADS slots, then hand the four sums to
-    // every rank of the cluster (all-to-all through distributed shared memory)
+    // block fold: G consecutive lanes own one cluster's THREADS slots (and clear them for the next
+    // pass), then hand the four sums to every rank of the cluster (all-to-all through DSMEM)
     const unsigned int par = it & 1u;
-    {
+    if (tid < G * KCAP) {  // whole warps
       const unsigned int cl = tid / G, sub = tid % G;
       long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll 4
       for (unsigned int u = sub; u < THREADS; u += G) {
         const int4 a = s_acc[cl * THREADS + u];
+        s_acc[cl * THREADS + u] = make_int4(0, 0, 0, 0);
         s0 += a.x;
         s1 += a.y;
         s2 += a.z;
@@ -266,49 +298,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
         dst[0] = make_longlong2(s0, s1);
         dst[1] = make_longlong2(s2, s3);
       }
-      if (tid < csize)
-        *cluster.map_shared_rank(s_x + ((size_t)par * csize + rank) * XS + KCAP * 4, tid) = (long long)s_slow;
+      if (warp == 0) {
+        const unsigned int sl = s_slow;
+        if (lane < csize) *cluster.map_shared_rank(s_x + ((size_t)par * csize + rank) * XS + KCAP * 4, lane) = (long long)sl;
+        __syncwarp();
+        if (lane == 0) s_slow = 0;
+      }
     }
+    KMG_TRACE_MARK();  // pass d: folded + sent
     cluster.sync();
+    KMG_TRACE_MARK();  // pass e: cluster barrier
 
-    // finalisation, redundantly and in the same fixed order in every CTA
+    // finalisation, redundantly and in the same fixed order in every warp of every CTA
     // (choose_centroid.wgsl:180-206; see finalize_pass)
     bool flag = false;
-    if (tid < k) {
+    if (lane < k) {
       long long s[4] = {0, 0, 0, 0};
       for (unsigned int r = 0; r < csize; ++r) {
-        const long long* a = s_x + ((size_t)par * csize + r) * XS + tid * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s[q] += a[q];
+        const longlong2* a = reinterpret_cast<const longlong2*>(s_x + ((size_t)par * csize + r) * XS + lane * 4);
+        const longlong2 a0 = a[0], a1 = a[1];
+        s[0] += a0.x;
+        s[1] += a0.y;
+        s[2] += a1.x;
+        s[3] += a1.y;
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) s_last[tid * 4 + q] = s[q];
+      for (int q = 0; q < 4; ++q) last[q] = s[q];
       if (s[3] > 0) {
         const double cnt = (double)s[3];
-        const float4 prev = s_cent[tid];
+        const float4 prev = my_cent[lane];
         float4 nc;
         nc.x = (float)(((double)s[0] / cnt) * (1.0 / 65536.0));
         nc.y = (float)(((double)s[1] / cnt) * (1.0 / 65536.0));
         nc.z = (float)(((double)s[2] / cnt) * (1.0 / 65536.0));
         nc.w = 1.0f;
-        s_cent[tid] = nc;
+        my_cent[lane] = nc;
         flag = ex::cie94(nc.x, nc.y, nc.z, prev.x, prev.y, prev.z) < prm.conv_threshold;
       }
     }
-    for (unsigned int r = 0; r < csize; ++r) slow_total += (unsigned long long)s_x[((size_t)par * csize + r) * XS + KCAP * 4];
-    conv = (unsigned int)__syncthreads_count(flag ? 1 : 0);
+    {
+      long long sl = lane < csize ? s_x[((size_t)par * csize + lane) * XS + KCAP * 4] : 0ll;
+      slow_total += (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned int)sl);
+    }
+    conv = __popc(__ballot_sync(0xffffffffu, flag));
     // core/src/modules.rs:802,827 — tested only when it > 0 && it % 8 == 0; also the hard cap.
     const bool check = it > 0 && prm.check_every != 0 && (it % prm.check_every) == 0;
     done = (check && conv >= k) || it + 1 >= prm.max_iter;
     ++it;
+    __syncwarp();
+    KMG_TRACE_MARK();  // pass f: finalised
   }
 
   // ---- results: centroids, state, table / dither threshold / RGBA8 palette for the remap --------
   if (rank == 0) {
-    if (tid < k) {
-      J.cent[tid] = s_cent[tid];
+    if (warp == 0 && lane < k) {
+      J.cent[lane] = my_cent[lane];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) J.last[tid * 4 + q] = s_last[tid * 4 + q];
+      for (int q = 0; q < 4; ++q) J.last[lane * 4 + q] = last[q];
     }
     if (tid == 0) {
       JobState* st = J.st;
@@ -325,6 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
     __syncthreads();
     build_table<THREADS>(J, k, prm.color_space, prm.want_palette != 0);
   }
+  KMG_TRACE_MARK();  // end
 }
 
 }  // namespace kmg
