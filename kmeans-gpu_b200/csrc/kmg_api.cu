@@ -994,7 +994,7 @@ static int resolve_seed(const kmg_opts& o, uint32_t gw, uint32_t gh, unsigned lo
 // and RGBA8 palette in every blob.  Asynchronous on s.
 static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uint8_t* d_rgba, uint32_t n_frames,
                                   uint32_t w, uint32_t h, uint32_t iw, uint32_t ih, uint32_t k, int cs, const kmg_opts& o,
-                                  void* blob, size_t blob_stride, kmg_job* job, cudaStream_t s) {
+                                  void* blob, size_t blob_stride, int tail, kmg_job* job, cudaStream_t s) {
   unsigned long long seed = 0;
   TRY(resolve_seed(o, iw, ih, &seed));
   job->ctx = ctx;
@@ -1021,7 +1021,7 @@ static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uin
   prm.check_every = o.check_every;
   prm.conv_threshold = o.convergence >= 0.0f ? o.convergence : (cs == KMG_LAB ? 1.0f : 0.01f);  // lib.rs:189-194
   prm.color_space = cs;
-  prm.want_palette = 1;
+  prm.tail = tail;
   prm.blob_stride = blob_stride;
   prm.lut = ctx->d_lut;
   return launch_small(ctx, plan, prm, job->P, n_frames, s);
@@ -1029,8 +1029,11 @@ static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uin
 
 // Returns with the job's final state on its way into ws->h_state (read it after the caller's
 // next stream synchronisation).  *prepared: the blob already holds table + palette for the remap.
+// What k_kmeans_small leaves in the blob besides the centroids (SmallParams::tail) for a remap mode.
+static int tail_for_mode(int mode) { return mode == KMG_DITHER ? 2 : (mode == KMG_REPLACE ? 1 : 0); }
+
 static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, uint32_t w, uint32_t h, uint32_t k,
-                            int cs, const kmg_opts& o, kmg_job* job, bool* prepared) {
+                            int cs, const kmg_opts& o, kmg_job* job, bool* prepared, int tail = 0) {
   cudaStream_t s = ws->stream;
   uint32_t iw = w, ih = h;
   const bool shrink = o.max_dim != 0 && (w > o.max_dim || h > o.max_dim);  // structures.rs:67-74
@@ -1040,7 +1043,7 @@ static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, 
   SmallPlan plan;
   if (!(o.flags & KMG_OPT_NO_FUSED_KMEANS) && small_plan(ctx, n, k, 1, &plan)) {
     job->h_state = ws->h_state;
-    TRY(kmeans_small_on_device(ctx, plan, d_rgba, 1, w, h, iw, ih, k, cs, o, ws->blob.p, 0, job, s));
+    TRY(kmeans_small_on_device(ctx, plan, d_rgba, 1, w, h, iw, ih, k, cs, o, ws->blob.p, 0, tail, job, s));
     CU(cudaMemcpyAsync(ws->h_state, job->P.st, sizeof(JobState), cudaMemcpyDeviceToHost, s));
     if (prepared) *prepared = true;
     return KMG_OK;
@@ -1130,7 +1133,7 @@ extern "C" int kmg_reduce(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_
   CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, s));
   kmg_job job;
   bool prepared = false;
-  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, &prepared));
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, &prepared, tail_for_mode(mode)));
   TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, h, mode, (uint8_t*)ws->out.p, s, prepared));
   CU(cudaMemcpyAsync(out_rgba, ws->out.p, bytes, cudaMemcpyDeviceToHost, s));
   if (centroids_out) CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, s));
@@ -1180,7 +1183,7 @@ static int reduce_batch_fused(kmg_ctx* ctx, const SmallPlan& plan, const uint8_t
                               uint8_t* d_out, void* blobs, float* centroids_out, uint32_t* passes_out, cudaStream_t s) {
   const size_t stride = batch_blob_stride(k);
   kmg_job job;
-  TRY(kmeans_small_on_device(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, o, blobs, stride, &job, s));
+  TRY(kmeans_small_on_device(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, o, blobs, stride, tail_for_mode(mode), &job, s));
   TRY(launch_remap(&job, d_rgba, w, h, mode, d_out, s, true, n_frames, stride));
   if (centroids_out)
     CU(cudaMemcpy2DAsync(centroids_out, (size_t)k * 16, job.P.cent, stride, (size_t)k * 16, n_frames, cudaMemcpyDeviceToHost, s));
@@ -1218,7 +1221,7 @@ extern "C" int kmg_dev_reduce_batch(kmg_ctx* ctx, const uint8_t* d_rgba, uint32_
     kmg_job job;
     bool prepared = false;
     const uint8_t* in = d_rgba + (size_t)f * frame_bytes;
-    TRY(kmeans_on_device(ctx, ws, in, w, h, k, cs, o, &job, &prepared));
+    TRY(kmeans_on_device(ctx, ws, in, w, h, k, cs, o, &job, &prepared, tail_for_mode(mode)));
     TRY(launch_remap(&job, in, w, h, mode, d_out + (size_t)f * frame_bytes, ws->stream, prepared));
     if (centroids_out)
       CU(cudaMemcpyAsync(centroids_out + (size_t)f * k * 4, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, ws->stream));

@@ -507,35 +507,56 @@ __global__ void __launch_bounds__(256) k_convert(const uint32_t* __restrict__ rg
 // ------------------------------------------------------------------------------------------------
 // K15: bilinear shrink, exact restatement (see oracle resize_image).  One destination pixel p of
 // the dw x dh image sampled from the sw x sh source: resize.wgsl:5-19 with a linear / clamp-to-edge
-// sampler at (gx/dw, gy/dh), unorm8 store.
-__device__ __forceinline__ uint32_t resize_pixel(const uint32_t* __restrict__ src, unsigned int sw, unsigned int sh,
-                                                 unsigned int dw, unsigned int dh, unsigned long long p) {
+// sampler at (gx/dw, gy/dh), unorm8 store.  Split into tap selection and blend so that callers can
+// keep the loads of several pixels in flight.
+struct ResizeTaps {
+  size_t i00, i10, i01, i11;  // source pixel indices
+  float fx, fy;               // blend weights of the second column / row
+};
+__device__ __forceinline__ ResizeTaps resize_taps(unsigned int sw, unsigned int sh, unsigned int dw, unsigned int dh,
+                                                  unsigned long long p) {
   unsigned int gx = (unsigned int)(p % dw), gy = (unsigned int)(p / dw);
   float py = fsub(fmul(fdiv((float)gy, (float)dh), (float)sh), 0.5f);
   float px = fsub(fmul(fdiv((float)gx, (float)dw), (float)sw), 0.5f);
   float fy0 = floorf(py), fx0 = floorf(px);
-  float fy = fsub(py, fy0), fx = fsub(px, fx0);
+  ResizeTaps t;
+  t.fy = fsub(py, fy0);
+  t.fx = fsub(px, fx0);
   long long y0 = (long long)fy0, x0 = (long long)fx0;
   long long y1 = y0 + 1, x1 = x0 + 1;
   y0 = min(max(y0, 0ll), (long long)sh - 1);
   y1 = min(max(y1, 0ll), (long long)sh - 1);
   x0 = min(max(x0, 0ll), (long long)sw - 1);
   x1 = min(max(x1, 0ll), (long long)sw - 1);
-  uint32_t p00 = __ldg(src + (size_t)y0 * sw + x0), p10 = __ldg(src + (size_t)y0 * sw + x1);
-  uint32_t p01 = __ldg(src + (size_t)y1 * sw + x0), p11 = __ldg(src + (size_t)y1 * sw + x1);
+  t.i00 = (size_t)y0 * sw + x0;
+  t.i10 = (size_t)y0 * sw + x1;
+  t.i01 = (size_t)y1 * sw + x0;
+  t.i11 = (size_t)y1 * sw + x1;
+  return t;
+}
+// u8f(v) must return fdiv((float)v, 255.0f) (directly, or from a table of those 256 quotients).
+template <class U8F>
+__device__ __forceinline__ uint32_t resize_blend(uint32_t p00, uint32_t p10, uint32_t p01, uint32_t p11, float fx, float fy,
+                                                 U8F u8f) {
   float wx0 = fsub(1.0f, fx), wy0 = fsub(1.0f, fy);
   uint32_t o = 0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    float c00 = fdiv((float)((p00 >> (8 * c)) & 255u), 255.0f);
-    float c10 = fdiv((float)((p10 >> (8 * c)) & 255u), 255.0f);
-    float c01 = fdiv((float)((p01 >> (8 * c)) & 255u), 255.0f);
-    float c11 = fdiv((float)((p11 >> (8 * c)) & 255u), 255.0f);
+    float c00 = u8f((p00 >> (8 * c)) & 255u);
+    float c10 = u8f((p10 >> (8 * c)) & 255u);
+    float c01 = u8f((p01 >> (8 * c)) & 255u);
+    float c11 = u8f((p11 >> (8 * c)) & 255u);
     float top = fadd(fmul(c00, wx0), fmul(c10, fx));
     float bot = fadd(fmul(c01, wx0), fmul(c11, fx));
     o |= ex::unorm8(fadd(fmul(top, wy0), fmul(bot, fy))) << (8 * c);
   }
   return o;
+}
+__device__ __forceinline__ uint32_t resize_pixel(const uint32_t* __restrict__ src, unsigned int sw, unsigned int sh,
+                                                 unsigned int dw, unsigned int dh, unsigned long long p) {
+  const ResizeTaps t = resize_taps(sw, sh, dw, dh, p);
+  return resize_blend(__ldg(src + t.i00), __ldg(src + t.i10), __ldg(src + t.i01), __ldg(src + t.i11), t.fx, t.fy,
+                      [](uint32_t v) { return fdiv((float)v, 255.0f); });
 }
 
 __global__ void __launch_bounds__(256) k_resize(const uint32_t* __restrict__ src, unsigned int sw, unsigned int sh,

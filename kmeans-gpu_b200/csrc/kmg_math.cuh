@@ -38,7 +38,7 @@ __device__ __forceinline__ float cie94_c(float l1, float a1, float b1, float c1,
   float dH = fsqrt(fmaxf(fsub(fadd(fmul(da, da), fmul(db, db)), fmul(dC, dC)), 0.0f));
   float SC = fadd(1.0f, fmul(0.045f, c1));
   float SH = fadd(1.0f, fmul(0.015f, c1));
-  float tL = fdiv(dL, 1.0f);
+  float tL = dL;  // dL / 1.0 (kL * SL = 1, delta_e.wgsl:17): x / 1 == x for every x, no division needed
   float tC = fdiv(dC, SC);
   float tH = fdiv(dH, SH);
   return fsqrt(fadd(fadd(fmul(tL, tL), fmul(tC, tC)), fmul(tH, tH)));
@@ -112,9 +112,21 @@ __device__ __forceinline__ uint32_t unorm8(float v) {
   if (v > 1.0f) v = 1.0f;
   return (uint32_t)__float2int_rn(fmul(v, 255.0f));
 }
+// pow_f32(t, 3.0f): the double product t*t*t is within 2.3e-16 of t^3; Ziv's test as in pow_third.
+__device__ __noinline__ float pow_cube_slow(float t) { return pow_f32(t, 3.0f); }
+__device__ __forceinline__ float pow_cube(float t) {
+  const double td = (double)t;
+  const double yd = td * td * td;
+  const float f = __double2float_rn(yd);
+  if (!(fabsf(f) > 1.0e-30f) || !(fabsf(f) < 1.0e30f)) return pow_cube_slow(t);  // zero, tiny, huge, NaN
+  const double h = (double)__int_as_float((__float_as_int(f) & 0x7f800000) - (24 << 23));
+  const double gap = fabs(fabs(yd - (double)f) - h);
+  if (gap < 1.0e-14 * fabs(yd) || (__float_as_int(f) & 0x007fffff) == 0) return pow_cube_slow(t);
+  return f;
+}
 // core/shaders/converters/lab_to_rgb.wgsl:40-66
 __device__ __forceinline__ float lab_finv(float t) {
-  float t3 = pow_f32(t, 3.0f);
+  float t3 = pow_cube(t);
   if (t3 > 0.008856f) return t3;
   return fdiv(fsub(t, 16.0f / 116.0f), 7.787f);
 }
@@ -123,7 +135,8 @@ __device__ __forceinline__ float srgb_encode(float c) {
   if (c > 0.0031308f) return fsub(fmul(1.055f, pow_f32(c, 1.0f / 2.4f)), 0.055f);
   return fmul(12.92f, c);
 }
-__device__ __forceinline__ uint32_t lab_to_rgba8(float L, float A, float B) {
+// Lab -> linear sRGB (lab_to_rgb.wgsl:40-82 up to the transfer function).
+__device__ __forceinline__ float3 lab_to_linear_rgb(float L, float A, float B) {
   float y = fdiv(fadd(L, 16.0f), 116.0f);
   float x = fadd(fdiv(A, 500.0f), y);
   float z = fsub(y, fdiv(B, 200.0f));
@@ -133,10 +146,15 @@ __device__ __forceinline__ uint32_t lab_to_rgba8(float L, float A, float B) {
   x = fdiv(x, 100.0f);
   y = fdiv(y, 100.0f);
   z = fdiv(z, 100.0f);
-  float r = fadd(fadd(fmul(3.2404542f, x), fmul(-1.5371385f, y)), fmul(-0.4985314f, z));
-  float g = fadd(fadd(fmul(-0.9692660f, x), fmul(1.8760108f, y)), fmul(0.0415560f, z));
-  float b = fadd(fadd(fmul(0.0556434f, x), fmul(-0.2040259f, y)), fmul(1.0572252f, z));
-  return unorm8(srgb_encode(r)) | (unorm8(srgb_encode(g)) << 8) | (unorm8(srgb_encode(b)) << 16) | 0xFF000000u;
+  float3 o;
+  o.x = fadd(fadd(fmul(3.2404542f, x), fmul(-1.5371385f, y)), fmul(-0.4985314f, z));
+  o.y = fadd(fadd(fmul(-0.9692660f, x), fmul(1.8760108f, y)), fmul(0.0415560f, z));
+  o.z = fadd(fadd(fmul(0.0556434f, x), fmul(-0.2040259f, y)), fmul(1.0572252f, z));
+  return o;
+}
+__device__ __forceinline__ uint32_t lab_to_rgba8(float L, float A, float B) {
+  const float3 c = lab_to_linear_rgb(L, A, B);
+  return unorm8(srgb_encode(c.x)) | (unorm8(srgb_encode(c.y)) << 8) | (unorm8(srgb_encode(c.z)) << 16) | 0xFF000000u;
 }
 // core/shaders/converters/rgb32f_to_rgb8u.wgsl:16-17 (alpha component w).
 __device__ __forceinline__ uint32_t rgbf_to_rgba8(float r, float g, float b, float w) {

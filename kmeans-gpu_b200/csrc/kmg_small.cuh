@@ -55,7 +55,7 @@ struct SmallParams {
   unsigned int max_iter, check_every;
   float conv_threshold;
   int color_space;
-  int want_palette;
+  int tail;                      // 0: centroids only, 1: + search table and RGBA8 palette, 2: + dither threshold
   size_t blob_stride;            // bytes between the job blobs of consecutive frames
   const float* lut;
 };
@@ -67,12 +67,26 @@ __host__ __device__ inline size_t small_smem_bytes(unsigned int ppc, unsigned in
   return (size_t)ppc * 20 + (size_t)kcap * threads * 16 + (size_t)2 * csize * small_xslots(kcap) * 8;
 }
 
+// Warp-wide maximum of a 64-bit key in two 32-bit hardware reductions (REDUX).
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long v) {
+  const unsigned int hi = (unsigned int)(v >> 32);
+  const unsigned int mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned int ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned int)v : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+// Warp-wide sum of 64-bit integers whose absolute values stay below 2^43: two 32-bit reductions.
+__device__ __forceinline__ long long warp_sum_split(long long v) {
+  const int hi = (int)(v >> 20);
+  const int lo = (int)(v & 0xfffff);
+  return ((long long)__reduce_add_sync(0xffffffffu, hi) << 20) + (long long)__reduce_add_sync(0xffffffffu, lo);
+}
+
 // KCAP: table / accumulator capacity (8, 16: saved-score search; 32: chunked search).
 template <int KCAP, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, JobPtrs J0) {
   static_assert(KCAP == 8 || KCAP == 16 || KCAP == 32, "table capacity");
   static_assert(THREADS % KCAP == 0, "fold groups");
-  constexpr int P = KCAP == 8 ? 4 : 2;
+  constexpr int P = 2;
   constexpr int G = THREADS / KCAP < 32 ? THREADS / KCAP : 32;  // lanes that fold one cluster's slots
   constexpr int NW = THREADS / 32;
   constexpr int TAB_BYTES = (KCAP / 8) * CHUNK_BYTES;
@@ -92,16 +106,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   float* s_dmin = reinterpret_cast<float*>(smem_raw + (size_t)ppc * 16);
   int4* s_acc = reinterpret_cast<int4*>(smem_raw + (size_t)ppc * 20);
   long long* s_x = reinterpret_cast<long long*>(smem_raw + (size_t)ppc * 20 + (size_t)KCAP * THREADS * 16);
-  // every warp keeps its own copy of the centroids and of the search table, so the finalisation
-  // of a pass needs no block-wide barrier (all warps compute identical values)
+  // every warp searches its own copy of the table (built redundantly from the shared centroids)
   __shared__ __align__(16) unsigned char s_tab_raw[NW][TAB_BYTES];
-  __shared__ float4 s_cent[NW][KCAP];
+  __shared__ float4 s_cent[KCAP];
+  __shared__ long long s_last[KCAP * 4];
+  __shared__ unsigned int s_flag[KCAP];
+  __shared__ unsigned int s_pal[KCAP];
   __shared__ float s_lut[256];
+  __shared__ float s_u8f[256];
   __shared__ unsigned long long s_keys[2][SMALL_MAX_CLUSTER];
   __shared__ unsigned long long s_red[NW];
   __shared__ unsigned int s_slow;
   CentRec* s_tab = reinterpret_cast<CentRec*>(s_tab_raw[warp]);
-  float4* my_cent = s_cent[warp];
 
   const JobPtrs J = job_at(J0, (size_t)frame * prm.blob_stride);
   const uint32_t* src = prm.src + (size_t)frame * prm.frame_px;
@@ -112,29 +128,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   KMG_TRACE_DECL;
   KMG_TRACE_MARK();  // 0: start
   // ---- shrink + convert into the local slice of the work plane --------------------------------
-  for (unsigned int c = tid; c < 256; c += THREADS) s_lut[c] = prm.lut[c];
+  for (unsigned int c = tid; c < 256; c += THREADS) {
+    s_lut[c] = prm.lut[c];
+    s_u8f[c] = fdiv((float)c, 255.0f);
+  }
+  if (tid < KCAP) s_flag[tid] = 0;
   if (tid == 0) s_slow = 0;
+  __syncthreads();
   {
-    // pass 1: RGBA8 of the clustered image (the loads of several pixels in flight), parked in the
-    // distance plane; pass 2: exact conversion (FP64 pow) out of shared memory
-    uint32_t* s_px = reinterpret_cast<uint32_t*>(s_dmin);
-#pragma unroll 4
-    for (unsigned int i = tid; i < n_local; i += THREADS)
-      s_px[i] = prm.shrink ? resize_pixel(src, prm.sw, prm.sh, prm.dw, prm.dh, first + i) : __ldg(src + first + i);
-    __syncthreads();
-    KMG_TRACE_MARK();  // 1: resized
-    for (unsigned int i = tid; i < n_local; i += THREADS) {
-      const uint32_t v = s_px[i];
-      s_work[i] = prm.color_space == 0
-                      ? ex::lin100_to_lab(s_lut[v & 255u], s_lut[(v >> 8) & 255u], s_lut[(v >> 16) & 255u])
-                      : ex::rgb8_to_rgbf(v);
+    // RGBA8 of the clustered image: taps of four pixels in flight per thread
+    auto to_work = [&](uint32_t v) -> float4 {
+      return prm.color_space == 0 ? ex::lin100_to_lab(s_lut[v & 255u], s_lut[(v >> 8) & 255u], s_lut[(v >> 16) & 255u])
+                                  : ex::rgb8_to_rgbf(v);
+    };
+    auto u8f = [&](uint32_t v) { return s_u8f[v]; };
+    constexpr int U = 4;
+    for (unsigned int i0 = tid; i0 < n_local; i0 += U * THREADS) {
+      uint32_t v[U];
+      if (prm.shrink) {
+        ResizeTaps t[U];
+        uint32_t tap[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned int i = min(i0 + u * THREADS, n_local - 1);
+          t[u] = resize_taps(prm.sw, prm.sh, prm.dw, prm.dh, first + i);
+          tap[u][0] = __ldg(src + t[u].i00);
+          tap[u][1] = __ldg(src + t[u].i10);
+          tap[u][2] = __ldg(src + t[u].i01);
+          tap[u][3] = __ldg(src + t[u].i11);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = resize_blend(tap[u][0], tap[u][1], tap[u][2], tap[u][3], t[u].fx, t[u].fy, u8f);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(src + first + min(i0 + u * THREADS, n_local - 1));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * THREADS < n_local) s_work[i0 + u * THREADS] = to_work(v[u]);
     }
   }
 #pragma unroll 4
   for (int q = 0; q < KCAP; ++q) s_acc[q * THREADS + tid] = make_int4(0, 0, 0, 0);
-  KMG_TRACE_MARK();  // 2: converted
+  KMG_TRACE_MARK();  // 1: converted
   cluster.sync();
-  KMG_TRACE_MARK();  // 3: cluster sync
+  KMG_TRACE_MARK();  // 2: cluster barrier
 
   // ---- farthest-point init (plus_plus_init.wgsl, kmeans++_calc_diff.wgsl) ----------------------
   auto pixel_colour = [&](unsigned int g) -> float4 {  // any pixel of the image, through DSMEM
@@ -144,8 +182,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
     return v;
   };
   float4 c = pixel_colour(prm.seed);
-  if (lane == 0) my_cent[0] = c;
-  if (tid == 0 && rank == 0) J.keys[0] = 0ull;
+  if (tid == 0) {
+    s_cent[0] = c;
+    if (rank == 0) J.keys[0] = 0ull;
+  }
   for (unsigned int j = 1; j < k; ++j) {
     const float cc = ex::chroma(c.y, c.z);
     unsigned long long best = 0ull;
@@ -157,70 +197,69 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
       const unsigned long long key = ((unsigned long long)__float_as_uint(dm) << 32) | (unsigned long long)((first + i) ^ 15u);
       best = key > best ? key : best;
     }
-    best = warp_max_u64(best);
+    best = warp_max_key(best);
     if (lane == 0) s_red[warp] = best;
     KMG_TRACE_MARK();  // init a: scanned
     __syncthreads();
-    KMG_TRACE_MARK();  // init b: block barrier
-    if (tid < csize) {  // thread r hands this CTA's maximum to rank r
-      unsigned long long b = s_red[0];
-#pragma unroll
-      for (int w = 1; w < NW; ++w) b = s_red[w] > b ? s_red[w] : b;
-      *cluster.map_shared_rank(&s_keys[j & 1u][rank], tid) = b;
+    if (warp == 0) {  // lane r hands this CTA's maximum to rank r
+      const unsigned long long b = warp_max_key(lane < NW ? s_red[lane] : 0ull);
+      if (lane < csize) *cluster.map_shared_rank(&s_keys[j & 1u][rank], lane) = b;
     }
-    KMG_TRACE_MARK();  // init c: sent
+    KMG_TRACE_MARK();  // init b: sent
     cluster.sync();
-    KMG_TRACE_MARK();  // init d: cluster barrier
-    unsigned long long gk = 0ull;
-    for (unsigned int r = 0; r < csize; ++r) gk = s_keys[j & 1u][r] > gk ? s_keys[j & 1u][r] : gk;
+    KMG_TRACE_MARK();  // init c: cluster barrier
+    const unsigned long long gk = warp_max_key(lane < csize ? s_keys[j & 1u][lane] : 0ull);
     c = pixel_colour((unsigned int)key_to_pixel(gk));
-    if (lane == 0) my_cent[j] = c;
-    if (tid == 0 && rank == 0) J.keys[j] = gk;
-    KMG_TRACE_MARK();  // init e: colour fetched
+    if (tid == 0) {
+      s_cent[j] = c;
+      if (rank == 0) J.keys[j] = gk;
+    }
+    KMG_TRACE_MARK();  // init d: colour fetched
   }
-  __syncwarp();
+  __syncthreads();
 
   // ---- Lloyd loop --------------------------------------------------------------------------------
   unsigned int it = 0, conv = 0;
   unsigned long long slow_total = 0;
-  long long last[4] = {0, 0, 0, 0};  // lane c: reduced sums of cluster c in the last pass
   bool done = false;
+  float lmax = 0.0f, cmax = 0.0f;
   const unsigned int tiles = (ppc + THREADS * P - 1) / (THREADS * P);
   while (true) {
     // this warp's table of the current centroids (KCAP <= 32 entries, one lane each)
-    float lmax = 0.0f, cmax = 0.0f;
-    if (lane < KCAP) {
-      CentRec r;
-      if (lane < k) {
-        const float4 v = my_cent[lane];
-        const float c2 = ex::chroma(v.y, v.z);
-        bool dup = false;
-        for (unsigned int i = 0; i < lane; ++i) {
-          const float4 u = my_cent[i];
-          dup |= (u.x == v.x && u.y == v.y && u.z == v.z);
-        }
-        r.q[0] = dup ? MASKED : 0.5f * (v.x * v.x);
-        r.q[1] = -v.x;
-        r.q[2] = 0.5f * (c2 * c2);
-        r.q[3] = c2;
-        r.q[4] = -v.y;
-        r.q[5] = -v.z;
-        lmax = fabsf(v.x);
-        cmax = c2;
-      } else {
-        r.q[0] = MASKED;
-        r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
-      }
-      *const_cast<CentRec*>(rec_at(s_tab, lane)) = r;
-    }
+    {
+      float lm = 0.0f, cm = 0.0f;
+      if (lane < KCAP) {
+        CentRec r;
+        if (lane < k) {
+          const float4 v = s_cent[lane];
+          const float c2 = ex::chroma(v.y, v.z);
+          bool dup = false;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-      cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+          for (unsigned int i = 0; i < KCAP - 1; ++i) {
+            const float4 u = s_cent[i];
+            dup |= (i < lane) && (u.x == v.x && u.y == v.y && u.z == v.z);
+          }
+          r.q[0] = dup ? MASKED : 0.5f * (v.x * v.x);
+          r.q[1] = -v.x;
+          r.q[2] = 0.5f * (c2 * c2);
+          r.q[3] = c2;
+          r.q[4] = -v.y;
+          r.q[5] = -v.z;
+          lm = fabsf(v.x);
+          cm = c2;
+        } else {
+          r.q[0] = MASKED;
+          r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
+        }
+        *const_cast<CentRec*>(rec_at(s_tab, lane)) = r;
+      }
+      // non-negative floats order like their bit patterns
+      lmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lm)));
+      cmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(cm)));
+      __syncwarp();
     }
-    __syncwarp();
     KMG_TRACE_MARK();  // pass a: table
-    if (done) break;  // the table of the final centroids is not needed (build_table below redoes it in HBM)
+    if (done) break;
 
     // assignment + thread-private accumulation over the local slice
     unsigned int slow = 0;
@@ -268,7 +307,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
     }
     KMG_TRACE_MARK();  // pass b: assigned
     __syncthreads();
-    KMG_TRACE_MARK();  // pass c: block barrier
 
     // block fold: G consecutive lanes own one cluster's THREADS slots (and clear them for the next
     // pass), then hand the four sums to every rank of the cluster (all-to-all through DSMEM)
@@ -285,12 +323,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
         s2 += a.z;
         s3 += a.w;
       }
+      if (G == 32) {
+        s0 = warp_sum_split(s0);
+        s1 = warp_sum_split(s1);
+        s2 = warp_sum_split(s2);
+        s3 = warp_sum_split(s3);
+      } else {
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        for (int o = G / 2; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        }
       }
       long long* mine = s_x + ((size_t)par * csize + rank) * XS + cl * 4;
       for (unsigned int r = sub; r < csize; r += G) {
@@ -298,66 +343,73 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
         dst[0] = make_longlong2(s0, s1);
         dst[1] = make_longlong2(s2, s3);
       }
-      if (warp == 0) {
-        const unsigned int sl = s_slow;
-        if (lane < csize) *cluster.map_shared_rank(s_x + ((size_t)par * csize + rank) * XS + KCAP * 4, lane) = (long long)sl;
-        __syncwarp();
-        if (lane == 0) s_slow = 0;
-      }
     }
-    KMG_TRACE_MARK();  // pass d: folded + sent
+    if (warp == NW - 1) {
+      const unsigned int sl = s_slow;
+      if (lane < csize) *cluster.map_shared_rank(s_x + ((size_t)par * csize + rank) * XS + KCAP * 4, lane) = (long long)sl;
+      __syncwarp();
+      if (lane == 0) s_slow = 0;
+    }
+    KMG_TRACE_MARK();  // pass c: folded + sent
     cluster.sync();
-    KMG_TRACE_MARK();  // pass e: cluster barrier
+    KMG_TRACE_MARK();  // pass d: cluster barrier
 
-    // finalisation, redundantly and in the same fixed order in every warp of every CTA
-    // (choose_centroid.wgsl:180-206; see finalize_pass)
-    bool flag = false;
-    if (lane < k) {
+    // finalisation (choose_centroid.wgsl:180-206; see finalize_pass): warp w reduces the partial
+    // sums of clusters w, w + NW, ... over the ranks in parallel lanes and publishes the new
+    // centroid; every CTA does the same work on the same numbers, so all CTAs stay identical
+    for (unsigned int cl = warp; cl < k; cl += NW) {
       long long s[4] = {0, 0, 0, 0};
-      for (unsigned int r = 0; r < csize; ++r) {
-        const longlong2* a = reinterpret_cast<const longlong2*>(s_x + ((size_t)par * csize + r) * XS + lane * 4);
+      if (lane < csize) {
+        const longlong2* a = reinterpret_cast<const longlong2*>(s_x + ((size_t)par * csize + lane) * XS + cl * 4);
         const longlong2 a0 = a[0], a1 = a[1];
-        s[0] += a0.x;
-        s[1] += a0.y;
-        s[2] += a1.x;
-        s[3] += a1.y;
+        s[0] = a0.x;
+        s[1] = a0.y;
+        s[2] = a1.x;
+        s[3] = a1.y;
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) last[q] = s[q];
-      if (s[3] > 0) {
+      for (int q = 0; q < 4; ++q) s[q] = warp_sum_split(s[q]);
+      bool flag = false;
+      const float4 prev = s_cent[cl];
+      __syncwarp();
+      if (s[3] > 0) {  // warp-uniform
         const double cnt = (double)s[3];
-        const float4 prev = my_cent[lane];
+        const long long mine = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+        const float comp = (float)(((double)mine / cnt) * (1.0 / 65536.0));
         float4 nc;
-        nc.x = (float)(((double)s[0] / cnt) * (1.0 / 65536.0));
-        nc.y = (float)(((double)s[1] / cnt) * (1.0 / 65536.0));
-        nc.z = (float)(((double)s[2] / cnt) * (1.0 / 65536.0));
+        nc.x = __shfl_sync(0xffffffffu, comp, 0);
+        nc.y = __shfl_sync(0xffffffffu, comp, 1);
+        nc.z = __shfl_sync(0xffffffffu, comp, 2);
         nc.w = 1.0f;
-        my_cent[lane] = nc;
         flag = ex::cie94(nc.x, nc.y, nc.z, prev.x, prev.y, prev.z) < prm.conv_threshold;
+        if (lane == 0) s_cent[cl] = nc;
       }
+      if (lane < 4) s_last[cl * 4 + lane] = s[lane];
+      if (lane == 0) s_flag[cl] = flag ? 1u : 0u;
     }
     {
-      long long sl = lane < csize ? s_x[((size_t)par * csize + lane) * XS + KCAP * 4] : 0ll;
+      const long long sl = lane < csize ? s_x[((size_t)par * csize + lane) * XS + KCAP * 4] : 0ll;
       slow_total += (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned int)sl);
     }
-    conv = __popc(__ballot_sync(0xffffffffu, flag));
+    __syncthreads();
+    conv = __popc(__ballot_sync(0xffffffffu, lane < k && s_flag[lane] != 0));
     // core/src/modules.rs:802,827 — tested only when it > 0 && it % 8 == 0; also the hard cap.
     const bool check = it > 0 && prm.check_every != 0 && (it % prm.check_every) == 0;
     done = (check && conv >= k) || it + 1 >= prm.max_iter;
     ++it;
-    __syncwarp();
-    KMG_TRACE_MARK();  // pass f: finalised
+    KMG_TRACE_MARK();  // pass e: finalised
   }
 
-  // ---- results: centroids, state, table / dither threshold / RGBA8 palette for the remap --------
+  // ---- results: centroids and state; for the remap also the table, RGBA8 palette and dither
+  //      threshold (k_prepare / build_table, spread over the threads of rank 0) -------------------
   if (rank == 0) {
-    if (warp == 0 && lane < k) {
-      J.cent[lane] = my_cent[lane];
+    JobState* st = J.st;
+    if (tid < k) {
+      J.cent[tid] = s_cent[tid];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) J.last[lane * 4 + q] = last[q];
+      for (int q = 0; q < 4; ++q) J.last[tid * 4 + q] = s_last[tid * 4 + q];
     }
     if (tid == 0) {
-      JobState* st = J.st;
       st->ticket = 0;
       st->conv = conv;
       st->passes = it;
@@ -367,9 +419,68 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
       st->check_every = prm.check_every;
       st->conv_threshold = prm.conv_threshold;
       st->slow_pixels = slow_total;
+      st->lmax = lmax;
+      st->cmax = cmax;
+      st->dither_threshold = 0.0f;
     }
-    __syncthreads();
-    build_table<THREADS>(J, k, prm.color_space, prm.want_palette != 0);
+    if (prm.tail >= 1) {
+      // warp 0's table holds the final centroids (the loop leaves after building it)
+      if (tid < pad32(k)) {
+        CentRec r;
+        if (tid < KCAP) {
+          r = *rec_at(reinterpret_cast<const CentRec*>(s_tab_raw[0]), tid);
+        } else {
+          r.q[0] = MASKED;
+          r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
+        }
+        J.tab[tid] = r;
+      }
+      // palette: one thread per (centroid, channel) — the transfer function is the expensive part
+      if (tid < k) s_pal[tid] = 0xFF000000u;
+      __syncthreads();
+      if (tid < 3 * k) {
+        const unsigned int cl = tid / 3, ch = tid % 3;
+        const float4 v = s_cent[cl];
+        unsigned int byte;
+        if (prm.color_space == 0) {
+          const float3 lin = ex::lab_to_linear_rgb(v.x, v.y, v.z);
+          byte = ex::unorm8(ex::srgb_encode(ch == 0 ? lin.x : (ch == 1 ? lin.y : lin.z)));
+        } else {
+          byte = ex::unorm8(ch == 0 ? v.x : (ch == 1 ? v.y : v.z));
+        }
+        atomicOr(&s_pal[cl], byte << (8 * ch));
+      }
+      // dither threshold (mix_colors.wgsl:53-68): all pair distances in parallel, then the greedy
+      // farthest-pair scan is a walk over a k x k table
+      float* s_pair = reinterpret_cast<float*>(s_acc);  // KCAP * KCAP floats
+      if (prm.tail >= 2 && k > 1) {
+        for (unsigned int e = tid; e < k * k; e += THREADS) {
+          const float4 ci = s_cent[e / k], cj = s_cent[e % k];
+          s_pair[e] = ex::cie94(ci.x, ci.y, ci.z, cj.x, cj.y, cj.z);  // centroid i first
+        }
+      }
+      __syncthreads();
+      if (tid < k) {
+        unsigned int pv = s_pal[tid];
+        if (prm.color_space != 0) pv = (pv & 0x00ffffffu) | (ex::unorm8(s_cent[tid].w) << 24);
+        J.pal[tid] = pv;
+      }
+      if (tid == 0 && prm.tail >= 2 && k > 1) {
+        unsigned int a = 0, b = 1;
+        float d_ab = s_pair[0 * k + 1];
+        for (unsigned int i = 2; i < k; ++i) {
+          const float da = s_pair[i * k + a], db = s_pair[i * k + b];
+          if (da > db && da > d_ab) {
+            d_ab = da;
+            b = i;
+          } else if (db > d_ab) {
+            d_ab = db;
+            a = i;
+          }
+        }
+        st->dither_threshold = fdiv(d_ab, fsqrt((float)k));
+      }
+    }
   }
   KMG_TRACE_MARK();  // end
 }

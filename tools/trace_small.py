@@ -17,18 +17,18 @@ lib = _native.load()
 lib.kmg_debug_small_trace.argtypes = [C.c_void_p]
 assert lib.kmg_debug_small_trace(buf.ctypes.data_as(C.c_void_p)) == 0
 t = buf.astype(np.int64)
-n_init = 5 * (k - 1)
-names = ["start", "resized", "converted", "csync"] + [f"init{j}.{p}" for j in range(1, k) for p in "abcde"]
-per_pass = ["table", "assigned", "bsync", "folded", "csync", "final"]
+n_init = 4 * (k - 1)
+names = ["start", "converted", "csync"] + [f"init{j}.{p}" for j in range(1, k) for p in "abcd"]
+per_pass = ["table", "assigned", "folded", "csync", "final"]
 names += [f"p{i}.{p}" for i in range(passes) for p in per_pass] + ["table_last", "end"]
 print("passes", passes, "marks", len(names))
 for r in (0, 7, 15):
     d = np.diff(t[r, :len(names)])
     print(f"rank {r}: total {t[r, len(names)-1]-t[r,0]} cycles")
-    print("  head:", {names[i + 1]: int(d[i]) for i in range(3)})
-    ini = d[3:3 + n_init].reshape(k - 1, 5) if k > 1 else np.zeros((0, 5))
-    print("  init mean per round [scan, bsync, send, csync, fetch]:", ini.mean(axis=0).round(0) if k > 1 else None)
-    ps = d[3 + n_init:3 + n_init + 6 * passes].reshape(passes, 6)
-    print("  pass mean [table, assign, bsync, fold+send, csync, finalise]:", ps.mean(axis=0).round(0), "sum", ps.mean(axis=0).sum().round(0))
+    print("  head:", {names[i + 1]: int(d[i]) for i in range(2)})
+    ini = d[2:2 + n_init].reshape(k - 1, 4) if k > 1 else np.zeros((0, 4))
+    print("  init mean per round [scan, bsync+send, csync, fetch]:", ini.mean(axis=0).round(0) if k > 1 else None)
+    ps = d[2 + n_init:2 + n_init + 5 * passes].reshape(passes, 5)
+    print("  pass mean [table, assign, bsync+fold+send, csync, finalise]:", ps.mean(axis=0).round(0), "sum", ps.mean(axis=0).sum().round(0))
     print("  first pass:", ps[0], " last:", ps[-1])
-    print("  tail:", d[3 + n_init + 6 * passes:])
+    print("  tail:", d[2 + n_init + 5 * passes:])
