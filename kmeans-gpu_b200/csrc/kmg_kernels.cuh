@@ -288,17 +288,25 @@ __device__ __forceinline__ void load_chunk(const CentRec* chunk, float (&f)[48])
   }
 }
 
-// Error bound of a score gap.  CONV (remap kernels): the pixel itself is approximate (fast Lab),
-// so the gap may additionally move by |grad d^2| * LAB_ERR summed over the two candidates:
-// |grad d^2| <= 2.5 * D_E, D_E <= SC * d  =>  conv_k * SC * sqrt(d^2) with conv_k = 5 * LAB_ERR and
-// d^2 = 2 * best score + the pixel-only part of the squared distance, L^2 + C^2 / SC^2.  Scores
-// are half distances, so the bound is halved as well.
+// Error bound of a score gap.  CONV (remap kernels): the pixel itself is approximate (fast Lab,
+// approximate chroma, dither offset added to the approximate value): |p~ - p| <= lab_err.  A score
+// gap between two candidates then moves by at most lab_err * (|grad s_c| + |grad s_c'|), s = d^2/2.
+// With tC = dC/SC, tH = dH/SH (both <= d = sqrt(d^2)), u = (a,b)/C1:
+//   d(dL^2)/dL           = 2 dL                                          <= 2 d
+//   d(tC^2)/d(a,b)       = 2 tC (1 - 0.045 tC) u / SC                    <= 2 d (1 + 0.045 d)
+//   d(dH^2/SH^2)/d(a,b)  = 2 (C2 u - (a2,b2)) / SH^2 - 0.03 tH^2 u / SH  <= 4 Cmax / SH^2 + 0.03 d^2
+// so |grad d^2| <= G(d) = 4 d + 0.12 d^2 + 4 Cmax / SH^2 for either candidate (their distances
+// differ by less than the bound being computed; d^2 is inflated by 2 eps0 and G by 2 %).
+// d^2 = 2 * best score + the pixel-only part of the squared distance, L^2 + C^2 / SC^2.
 template <bool CONV>
-__device__ __forceinline__ float total_eps(float eps0, float m, float conv_k, float L, float C, float inv_sc2) {
+__device__ __forceinline__ float total_eps(float eps0, float m, float lab_err, float L, float C, float inv_sc2, float hs,
+                                           float cmax) {
   if (!CONV) return eps0;
   const float pconst = fmaf(L, L, C * C * inv_sc2);
-  const float SC = fmaf(0.045f, C, 1.0f);
-  return eps0 + 0.5f * conv_k * SC * fast::sqrt_approx(fmaxf(fmaf(2.0f, m, pconst), 0.0f) + 2.0f * eps0) + 1.5e-6f;
+  const float d2 = fmaxf(fmaf(2.0f, m, pconst), 0.0f) + 2.0f * eps0;
+  const float d = fast::sqrt_approx(d2);
+  const float G = fmaf(d, 4.0f, fmaf(0.12f, d2, 4.0f * cmax * hs));
+  return fmaf(1.02f * lab_err, G, eps0) + 1.5e-6f;
 }
 
 // Small tables (KT = 8 or 16, compile time): all KT scores of a pixel stay in registers.
@@ -309,13 +317,15 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::f32x2 pp[H][5];
-  float inv_sc2[P];
+  float inv_sc2[P], inv_sh2[P];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
     const fast::PixCoef c0 = fast::pix_coef(px.L[2 * h], px.a[2 * h], px.b[2 * h], px.C[2 * h]);
     const fast::PixCoef c1 = fast::pix_coef(px.L[2 * h + 1], px.a[2 * h + 1], px.b[2 * h + 1], px.C[2 * h + 1]);
     inv_sc2[2 * h] = c0.p1;
     inv_sc2[2 * h + 1] = c1.p1;
+    inv_sh2[2 * h] = c0.hs;
+    inv_sh2[2 * h + 1] = c1.hs;
     pack_coefs(c0, c1, pp[h]);
   }
   fast::f32x2 s2[KT][H];
@@ -343,9 +353,9 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
     ma = fminf(ma, sa[KT - 1]);
     mb = fminf(mb, sb[KT - 1]);
     eps[2 * h] = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, conv_k, px.L[2 * h],
-                                 px.C[2 * h], inv_sc2[2 * h]);
+                                 px.C[2 * h], inv_sc2[2 * h], inv_sh2[2 * h], cmax);
     eps[2 * h + 1] = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, conv_k,
-                                     px.L[2 * h + 1], px.C[2 * h + 1], inv_sc2[2 * h + 1]);
+                                     px.L[2 * h + 1], px.C[2 * h + 1], inv_sc2[2 * h + 1], inv_sh2[2 * h + 1], cmax);
     certify_pair<KT>(sa, sb, ma, mb, eps[2 * h], eps[2 * h + 1], certified[2 * h], certified[2 * h + 1], idx[2 * h],
                      idx[2 * h + 1]);
   }
@@ -416,9 +426,9 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
     }
     const float ma = tournament8(sa), mb = tournament8(sb);
     const float ea = total_eps<CONV>(fast::score_eps(px.L[2 * h], px.C[2 * h], lmax, cmax), ma, conv_k, px.L[2 * h],
-                                     px.C[2 * h], pc[2 * h].p1);
+                                     px.C[2 * h], pc[2 * h].p1, pc[2 * h].hs, cmax);
     const float eb = total_eps<CONV>(fast::score_eps(px.L[2 * h + 1], px.C[2 * h + 1], lmax, cmax), mb, conv_k,
-                                     px.L[2 * h + 1], px.C[2 * h + 1], pc[2 * h + 1].p1);
+                                     px.L[2 * h + 1], px.C[2 * h + 1], pc[2 * h + 1].p1, pc[2 * h + 1].hs, cmax);
     bool ca, cb;
     unsigned int ia, ib;
     certify_pair<8>(sa, sb, ma, mb, ea, eb, ca, cb, ia, ib);
@@ -963,6 +973,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t
   for (unsigned int c = tid; c < 256; c += THREADS) lut[c] = lut_g[c];
   const float lmax = st->lmax, cmax = st->cmax;
   const float thr = st->dither_threshold;
+  const unsigned long long w_magic = ~0ull / w + 1ull;
   __syncthreads();
 
   constexpr int P = 4;
@@ -996,9 +1007,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t
     Pix<P> px;
     float off[P];
     unsigned int x = 0, y = 0;
-    if (MODE == 1) {
-      x = (unsigned int)(p0 % w);
-      y = (unsigned int)(p0 / w);
+    if (MODE == 1) {  // p0 / w by multiplication with ceil(2^64 / w): exact for p0 < 2^33
+      y = w == 1 ? (unsigned int)p0 : (unsigned int)__umul64hi(p0, w_magic);
+      x = (unsigned int)(p0 - (unsigned long long)y * w);
     }
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -1016,10 +1027,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t
       off[i] = 0.0f;
       if (MODE == 1) {
         unsigned int xi = x + i, yi = y;
-        if (xi >= w) {  // group straddles a row end (w % 4 != 0)
-          unsigned long long p = p0 + i;
-          xi = (unsigned int)(p % w);
-          yi = (unsigned int)(p / w);
+        while (xi >= w) {  // group straddles a row end (w % 4 != 0)
+          xi -= w;
+          ++yi;
         }
         float iv = c_bayer[(xi & 3u) + ((yi & 3u) << 2)] * 0.0625f - 0.5f;  // mix_colors.wgsl:21-27,70
         off[i] = fmul(thr, iv);
@@ -1032,7 +1042,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t
       px.b[i] = b;
       px.C[i] = fast::sqrt_approx(fmaf(a, a, b * b));
     }
-    const float conv_k = color_space == 0 ? 5.0f * fast::LAB_ERR : 5.0f * 2.4e-7f;
+    const float conv_k = color_space == 0 ? fast::LAB_ERR : fast::RGB_ERR;  // |approximate pixel - exact pixel|
     float eps[P];
     unsigned int idx[P];
     bool certified[P];

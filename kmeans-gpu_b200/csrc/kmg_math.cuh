@@ -231,6 +231,7 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
 // is the first coefficient and no sign or factor 2 is ever applied per pixel (10 operations).
 struct PixCoef {
   float p0, p1, p2, p3, p4;
+  float hs;  // 1 / SH^2
 };
 __device__ __forceinline__ PixCoef pix_coef(float L, float a, float b, float C1) {
   float SC = fmaf(0.045f, C1, 1.0f);
@@ -240,6 +241,7 @@ __device__ __forceinline__ PixCoef pix_coef(float L, float a, float b, float C1)
   PixCoef p;
   p.p1 = rSC * rSC;
   float hs = rSH * rSH;
+  p.hs = hs;
   p.p0 = L;
   p.p2 = C1 * (hs - p.p1);
   p.p3 = hs * a;
@@ -282,9 +284,18 @@ __device__ __forceinline__ float3 lin100_to_lab(float r, float g, float b) {
   o.z = 200.0f * (y - z);
   return o;
 }
-// Bound on |fast Lab - exact Lab| (Euclidean norm); measured max is ~2e-4 over all 2^24 colours
-// (tests/test_gpu_parity.py::test_fast_lab_error), the bound keeps a 5x margin.
-constexpr float LAB_ERR = 1.0e-3f;
+// Bound on |approximate pixel - exact pixel| (Euclidean norm) in the remap kernels:
+//   9.92e-5  largest |fast Lab - exact Lab| over ALL 2^24 sRGB colours (exhaustive on B200, the MUFU
+//            results being deterministic; tests/test_gpu_parity.py::test_fast_lab_error_bound)
+// + 1.4e-5   the dither offset is added to the approximate value and to the exact one: two
+//            roundings of at most half an ulp(128) = 2^-18 per component
+// + 2.4e-5   the chroma handed to the score is sqrt.approx (2^-23 relative) of a rounded a^2 + b^2,
+//            C <= 134
+// = 1.37e-4, rounded up.
+constexpr float LAB_ERR = 1.5e-4f;
+// RGB colour space: v * (1/255) against the exact v / 255 (one ulp of 1.0 per component), plus the
+// same two terms for values <= 1.
+constexpr float RGB_ERR = 6.0e-7f;
 
 }  // namespace fast
 }  // namespace kmg
