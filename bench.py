@@ -51,7 +51,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons under load.  nvidia-smi needs a few hundred ms to start
+    and the timed region may be shorter than that, so the sampler is started before the warm-up and
+    every line is stamped on arrival: stop() reports the samples that fall inside the timed window
+    and, when there are fewer than two, all samples taken under the (identical) warm-up load too."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -59,27 +62,35 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (arrival time, text)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self) -> int:
+        return len(self.lines)
+
+    def stop(self, t_begin: float, t_end: float, t_load: float):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [ln for (t, ln) in self.lines if t_begin <= t <= t_end + 0.02]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [ln for (t, ln) in self.lines if t_load <= t <= t_end + 0.02]
+            window = "warm-up + timed region (same load; the timed region is shorter than two sampling periods)"
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -92,7 +103,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_iteration_sample(side: int, steps: int):
@@ -123,7 +134,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} blobs({BLOBS}) k={K_CLUSTERS} Lab assign+update iteration", "k": K_CLUSTERS},
+        "config": {"workload": f"{W}x{H} blobs({BLOBS}) k={K_CLUSTERS} Lab assign+update iteration per GPU", "k": K_CLUSTERS,
+                   "bytes_per_px": BYTES_PER_PX},
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": "port",
                          "sample": f"{side}x{side} crop of the same synthetic image, {steps} iterations, "
                                    "oracle/oracle.cpp (restated reference; Rust+wgpu reference not buildable here)"},
@@ -171,16 +183,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        job.step(1)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_load = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        job.step(1)
+    # keep the same load running (untimed) until the clock sampler delivers, at most ~1.5 s
+    flag = torch.zeros(1, device=dev)
+    while True:
+        if rank == 0:
+            flag[0] = 1.0 if (sampler.count() >= 3 or time.perf_counter() - t_load > 1.5 or sampler.proc is None) else 0.0
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if float(flag[0]) > 0:
+            break
+        job.step(20)
+        torch.cuda.synchronize()
+    barrier()
     launches0 = proc.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.perf_counter()
     t_start.record()
     for a, b in evs:
         a.record()
@@ -188,20 +213,21 @@ def run_ours(args):
         b.record()
     t_end.record()
     barrier()
+    t_wall1 = time.perf_counter()
     launches = proc.launch_count() - launches0
     total_ms = t_start.elapsed_time(t_end)
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1, t_load) if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms, step_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, step_ms = float(t[0]), float(t[1])
-    stats = job.stats()
 
     # ---- end to end through the host C ABI (pinned host image) --------------------------------
     host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     host.copy_(img)
     torch.cuda.synchronize()
+    stats = job.stats()
     e2e_opts = K.Opts(max_dim=0, max_iter=E2E_PASSES, check_every=0)
     host_np = host.numpy()
     e2e_steps = max(1, min(args.steps, 3))
@@ -218,6 +244,31 @@ def run_ours(args):
         e2e_s = float(t[0])
     e2e_mpix = world * n * E2E_PASSES * e2e_steps / e2e_s / 1e6
 
+    # config 4 on this GPU's share: k = 256 iteration over the same plane
+    job.close()
+    del work, host, img
+    img = D.synth(proc, n, first_pixel=rank * n, seed=SEED, blobs=512, device=dev).view(H, W, 4)
+    work = D.convert(proc, img)
+    job256 = D.Job(proc, work, W, H, 256, opts=opts)
+    job256.init()
+    for _ in range(2):
+        job256.step(1)
+    torch.cuda.synchronize()
+    a256, b256 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a256.record()
+    job256.step(3)
+    b256.record()
+    torch.cuda.synchronize()
+    ms256 = a256.elapsed_time(b256) / 3
+    st256 = job256.stats()
+    job256.close()
+    del work, img
+    torch.cuda.empty_cache()
+    extras = run_extras(proc, K, D, torch, dev, world, rank, dist if world > 1 else None)
+    extras["iteration_k256_8192"] = {"mpix_per_s_per_gpu": n / ms256 / 1e3, "ms_per_pass": ms256,
+                                     "exact_path_pixels_per_pass": st256["slow_pixels"] / max(st256["passes"], 1),
+                                     "what": "8192x8192 blobs(512) k=256 assign+update pass on one GPU (config 4 without the all-reduce)"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = n * BYTES_PER_PX / (step_ms * 1e-3) / 1e9
@@ -228,8 +279,13 @@ def run_ours(args):
                 traffic = json.loads(tp.read_text()).get("lloyd_k8_8192_bytes_per_launch")
             except Exception:
                 traffic = None
-        extras = run_extras(proc, K, D, torch, dev)
-        cpu_mpix, cpu_threads, cpu_sec = cpu_iteration_sample(2048, 3)
+        if world == 1:
+            cpu_mpix, cpu_threads, cpu_sec = cpu_iteration_sample(2048, 3)
+            cpu_baseline = {"value": cpu_mpix, "unit": "Mpix/s", "cores": cpu_threads, "kind": "port",
+                            "sample": "2048x2048 crop of the same synthetic image, 3 iterations, oracle/oracle.cpp "
+                                      "(restated reference on the host CPU; not wgpu/lavapipe)"}
+        else:
+            cpu_baseline = None  # reported at N=1 only
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3) / 1e6, "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -239,11 +295,9 @@ def run_ours(args):
                        "k": K_CLUSTERS, "bytes_per_px": BYTES_PER_PX, "l2": "work plane 1 GiB per GPU > 126 MB L2",
                        "exact_path_pixels_per_pass": stats["slow_pixels"] / max(stats["passes"], 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd<8,8,256,4,true,2>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd<KT=8,KCAP=8,256 threads,4 px/thread,private accumulators,2 blocks/SM>",
                          "kernel_ms": step_ms},
-            "cpu_baseline": {"value": cpu_mpix, "unit": "Mpix/s", "cores": cpu_threads, "kind": "port",
-                             "sample": "2048x2048 crop of the same synthetic image, 3 iterations, oracle/oracle.cpp "
-                                       "(restated reference on the host CPU; not wgpu/lavapipe)"},
+            "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": K_CLUSTERS * 16 + 64,
                     "call": f"kmg_kmeans_palette(max_dim=0, {E2E_PASSES} passes) on a pinned host image", "steps": e2e_steps},
             "gpu_launches": int(launches),
@@ -251,51 +305,128 @@ def run_ours(args):
             "extras": extras,
         }
         print(json.dumps(line))
-    job.close()
     proc.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_extras(proc, K, D, torch, dev):
-    """End-to-end images/s through the host API for the small configs (bounded, a few seconds)."""
+def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
+    """The other BASELINE configs, bounded to a few seconds each.  Device-side numbers are CUDA-event
+    timed on the launching stream; end-to-end numbers are wall clock around the public host call with
+    page-locked buffers (H2D + kernels + D2H inside).  With N ranks every rank runs its own share and
+    the slowest rank's time counts."""
     import oracle_lib as O
     from PIL import Image as PILImage
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return x
+
+    def ev_ms(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
     out = {}
+    # ---- configs 1-2: tokyo reduce -c 8 -m dither + palette -c 8, host image in, host image out ----
     tokyo = np.array(PILImage.open(ROOT / "tests" / "golden" / "tokyo.png").convert("RGBA"))
-    tk = torch.from_numpy(tokyo).pin_memory().numpy()
-    for _ in range(2):
-        proc.reduce(8, tk, reduce_mode=K.ReduceMode.Dither)
+    tk = K.pinned_empty(tokyo.shape)
+    tk[...] = tokyo
+    tk_out = K.pinned_empty(tokyo.shape)
+    for _ in range(3):
+        proc.reduce(8, tk, reduce_mode=K.ReduceMode.Dither, out=tk_out)
         proc.palette(8, tk)
-    reps = 10
+    reps = 50
     t0 = time.perf_counter()
     for _ in range(reps):
-        proc.reduce(8, tk, reduce_mode=K.ReduceMode.Dither)
-        proc.palette(8, tk)
-    dt = (time.perf_counter() - t0) / reps
-    out["tokyo_reduce_dither_plus_palette_c8"] = {"images_per_s": 1.0 / dt, "ms": dt * 1e3, "h2d_bytes": int(tokyo.nbytes) * 2}
+        proc.reduce(8, tk, reduce_mode=K.ReduceMode.Dither, out=tk_out)
+    t_reduce = (time.perf_counter() - t0) / reps
     t0 = time.perf_counter()
-    O.reduce(tokyo, 8, "dither")
-    O.palette(tokyo, 8)
-    out["tokyo_reduce_dither_plus_palette_c8"]["cpu_oracle_images_per_s"] = 1.0 / (time.perf_counter() - t0)
-    # config 5: 1080p frames, k=16 reduce+dither, frames resident in HBM
-    nf = 16
+    for _ in range(reps):
+        proc.palette(8, tk)
+    t_pal = (time.perf_counter() - t0) / reps
+    entry = {"images_per_s": 1.0 / (t_reduce + t_pal), "reduce_dither_us": t_reduce * 1e6, "palette_us": t_pal * 1e6,
+             "h2d_bytes": int(tokyo.nbytes) * 2, "d2h_bytes": int(tokyo.nbytes) + 8 * 16,
+             "launches_per_reduce": 2, "what": "ImageProcessor.reduce(8, dither) + .palette(8), pinned host buffers"}
+    if rank == 0 and world == 1:
+        t0 = time.perf_counter()
+        O.reduce(tokyo, 8, "dither")
+        O.palette(tokyo, 8)
+        entry["cpu_oracle_images_per_s"] = 1.0 / (time.perf_counter() - t0)
+        entry["cpu_oracle_threads"] = O.num_threads()
+    out["tokyo_reduce_dither_plus_palette_c8"] = entry
+
+    # ---- config 3: find, 64-colour resurrect palette, dither, synthetic 4K (uniform colours) --------
+    pal = K.parse_palette(ROOT / "tests" / "golden" / "resurrect_64.png")
+    cent64 = K.fixed_centroids(pal)
+    w4, h4 = 3840, 2160
+    img4 = D.synth(proc, w4 * h4, seed=1, blobs=0, device=dev).view(h4, w4, 4)
+    out4 = torch.empty_like(img4)
+    tiny = torch.empty((8, 4), dtype=torch.float32, device=dev)
+    job64 = D.Job(proc, tiny, 8, 1, 64)
+    job64.set_centroids(cent64)
+    for _ in range(3):
+        job64.remap(img4, K.ReduceMode.Dither, out=out4)
+    ms = ev_ms(lambda: job64.remap(img4, K.ReduceMode.Dither, out=out4), 20)
+    h4in = K.pinned_empty((h4, w4, 4))
+    h4in[...] = img4.cpu().numpy()
+    h4out = K.pinned_empty((h4, w4, 4))
+    proc.find(h4in, pal, K.ReduceMode.Dither, out=h4out)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        proc.find(h4in, pal, K.ReduceMode.Dither, out=h4out)
+    t_find = (time.perf_counter() - t0) / 5
+    out["find_dither_resurrect64_4k"] = {"mpix_per_s_resident": w4 * h4 / ms / 1e3, "kernel_ms": ms,
+                                         "gb_per_s_8B_per_px": 8 * w4 * h4 / ms / 1e6,
+                                         "e2e_images_per_s": 1.0 / t_find, "e2e_mpix_per_s": w4 * h4 / t_find / 1e6}
+    job64.close()
+
+    # ---- config 5: 1920x1080 frames, k=16 reduce + dither --------------------------------------------
+    nf = 192
     frames = torch.empty((nf, 1080, 1920, 4), dtype=torch.uint8, device=dev)
     for f in range(nf):
-        D.synth(proc, 1920 * 1080, frame=f, seed=3, blobs=32, out=frames[f].view(-1, 4))
+        D.synth(proc, 1920 * 1080, frame=rank * nf + f, seed=3, blobs=32, out=frames[f].view(-1, 4))
     outb = torch.empty_like(frames)
-    D.reduce_batch(proc, frames[:2], 16, K.ReduceMode.Dither, out=outb[:2])
+    D.reduce_batch(proc, frames, 16, K.ReduceMode.Dither, out=outb)  # warm-up (workspace allocation)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    D.reduce_batch(proc, frames, 16, K.ReduceMode.Dither, out=outb)
+    _, _, passes = D.reduce_batch(proc, frames, 16, K.ReduceMode.Dither, out=outb)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["frames_1080p_k16_reduce_dither_resident"] = {"images_per_s": nf / dt, "frames": nf}
+    dt = max_over_ranks(time.perf_counter() - t0)
+    entry = {"images_per_s": world * nf / dt, "frames_per_gpu": nf, "mean_passes": float(passes.mean()),
+             "launches": 2, "what": "kmg_dev_reduce_batch: one cluster launch + one remap launch for all frames"}
+    hn = 96
+    hin = K.pinned_empty((hn, 1080, 1920, 4))
+    hin[...] = frames[:hn].cpu().numpy()
+    hout = K.pinned_empty((hn, 1080, 1920, 4))
+    del frames, outb
+    proc.reduce_batch(16, hin[:32], K.ReduceMode.Dither, out=hout[:32])
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    proc.reduce_batch(16, hin, K.ReduceMode.Dither, out=hout)
+    dt = max_over_ranks(time.perf_counter() - t0)
+    entry["e2e_images_per_s"] = world * hn / dt
+    entry["e2e_bytes_per_frame_each_way"] = 1920 * 1080 * 4
+    entry["e2e_what"] = f"kmg_reduce_batch on {hn} pinned host frames per GPU: chunked H2D / kernels / D2H pipeline"
+    out["frames_1080p_k16_reduce_dither"] = entry
     return out
 
 
 def main():
+    # the CPU legs use every host core, also under torchrun (which exports OMP_NUM_THREADS=1);
+    # libgomp reads the variable when the oracle library is loaded
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -116,6 +116,13 @@ int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_frames, uint3
                      int color_space, int mode, const kmg_opts* opts, uint8_t* out_rgba, float* centroids_out,
                      uint32_t* passes_out);
 
+/* Page-locked host buffers.  The reference hands wgpu pageable slices (queue.write_texture,
+ * core/src/structures.rs:47-63); with CUDA the host<->device copies of a call only run at full PCIe
+ * speed, and the chunks of kmg_reduce_batch only overlap, when the caller's buffers are page-locked.
+ * Optional: every entry point accepts pageable memory as well. */
+void* kmg_alloc_pinned(size_t bytes);
+void kmg_free_pinned(void* p);
+
 /* ---- host-side colour helpers (CPU in the reference too: `palette` crate 0.7.3) -------------- */
 
 /* CentroidsBuffer::fixed_centroids (core/src/structures.rs:523-553): sRGB8 -> k x 4 floats. */

@@ -16,12 +16,13 @@ from .processor import (  # noqa: F401
     centroids_to_rgba8,
     sort_palette_by_lightness,
     resized_dims,
+    pinned_empty,
 )
 from .palette import parse_colors, parse_palette, validate_palette  # noqa: F401
 from .sharding import row_shards, frame_shards  # noqa: F401
 
 __all__ = [
     "Algorithm", "ColorSpace", "Image", "ImageProcessor", "KmgError", "Opts", "ReduceMode",
-    "fixed_centroids", "centroids_to_rgba8", "sort_palette_by_lightness", "resized_dims",
+    "fixed_centroids", "centroids_to_rgba8", "sort_palette_by_lightness", "resized_dims", "pinned_empty",
     "parse_colors", "parse_palette", "validate_palette", "row_shards", "frame_shards",
 ]

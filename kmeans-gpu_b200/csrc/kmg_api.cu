@@ -464,6 +464,19 @@ extern "C" void kmg_destroy(kmg_ctx* ctx) {
   delete ctx;
 }
 
+extern "C" void* kmg_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    fail(KMG_ERR_OOM, "kmg_alloc_pinned(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void kmg_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 extern "C" uint64_t kmg_launch_count(kmg_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 extern "C" void kmg_resized_dims(uint32_t w, uint32_t h, uint32_t max_size, uint32_t* ow, uint32_t* oh) {
@@ -1254,7 +1267,9 @@ extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_fr
   // Chunks of frames flow through up to three workspaces (stream + buffers each): the upload of
   // chunk i+1 and the read-back of chunk i-1 overlap the kernels of chunk i.  Overlap needs the
   // caller's buffers to be page-locked; pageable buffers still work, the copies then serialise.
-  const uint32_t chunk = (uint32_t)std::min<size_t>(n_frames, std::max<size_t>(16, ((size_t)128 << 20) / frame_bytes));
+  // ~64 MiB per chunk: large enough for full-rate DMA, small enough that filling and draining the
+  // pipeline costs little; at least 8 frames so the cluster launch still covers the SMs
+  const uint32_t chunk = (uint32_t)std::min<size_t>(n_frames, std::max<size_t>(8, ((size_t)64 << 20) / frame_bytes));
   const uint32_t n_chunks = (n_frames + chunk - 1) / chunk;
   const uint32_t n_ws = std::min<uint32_t>(3, n_chunks);
   Workspace* wss[3] = {nullptr, nullptr, nullptr};

@@ -150,6 +150,31 @@ def resized_dims(w: int, h: int, max_size: int = 256):
     return ow.value, oh.value
 
 
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """A numpy array in page-locked host memory (kmg_alloc_pinned): host<->device copies of such
+    buffers run at full PCIe speed and overlap with kernels.  Freed when the array is collected."""
+    import weakref
+
+    lib = _native.load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    ptr = lib.kmg_alloc_pinned(max(n, 1))
+    if not ptr:
+        raise KmgError(3, lib.kmg_last_error().decode("utf-8", "replace"))
+    buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.kmg_free_pinned, ptr)
+    return arr
+
+
+def _out_image(out, h, w):
+    if out is None:
+        return np.empty((h, w, 4), np.uint8)
+    if out.dtype != np.uint8 or out.shape != (h, w, 4) or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out must be a contiguous uint8 array of shape {(h, w, 4)}")
+    return out
+
+
 class ImageProcessor:
     """core/src/lib.rs:24-165.  One instance may be shared by many threads
     (core/examples/parallel.rs:23,36-51)."""
@@ -201,21 +226,22 @@ class ImageProcessor:
         return sort_palette_by_lightness(centroids_to_rgba8(cent, color_space))
 
     def find(self, image, colors, reduce_mode: ReduceMode = ReduceMode.Replace,
-             color_space: ColorSpace = ColorSpace.Lab) -> Image:
+             color_space: ColorSpace = ColorSpace.Lab, out: np.ndarray | None = None) -> Image:
         """lib.rs:79-114: remap onto a fixed palette given as RGBA8 colours."""
         cent = fixed_centroids(colors, color_space)
-        return self.remap(image, cent, reduce_mode, color_space)
+        return self.remap(image, cent, reduce_mode, color_space, out=out)
 
     def reduce(self, color_count: int, image, algo: Algorithm = Algorithm.Kmeans,
                reduce_mode: ReduceMode = ReduceMode.Replace, opts: Opts | None = None,
-               color_space: ColorSpace = ColorSpace.Lab, return_details: bool = False):
-        """lib.rs:116-164."""
+               color_space: ColorSpace = ColorSpace.Lab, return_details: bool = False,
+               out: np.ndarray | None = None):
+        """lib.rs:116-164.  `out`: optional (h, w, 4) uint8 result buffer (e.g. from pinned_empty)."""
         if algo is not Algorithm.Kmeans:
             raise KmgError(5, "Algorithm::Octree is the reference's CPU quantiser (core/src/octree.rs); "
                               "feed its palette to find() instead")
         img = _as_image(image)
         w, h = img.dimensions
-        out = np.empty((h, w, 4), np.uint8)
+        out = _out_image(out, h, w)
         cent = np.empty((int(color_count), 4), np.float32) if color_count > 0 else np.empty((0, 4), np.float32)
         passes = C.c_uint32(0)
         o = (opts or Opts()).to_c()
@@ -241,12 +267,12 @@ class ImageProcessor:
         return cent, passes.value
 
     def remap(self, image, centroids, reduce_mode: ReduceMode = ReduceMode.Replace,
-              color_space: ColorSpace = ColorSpace.Lab) -> Image:
+              color_space: ColorSpace = ColorSpace.Lab, out: np.ndarray | None = None) -> Image:
         """operations::{find_colors,dither_colors,meld_colors} (operations.rs:99-271)."""
         img = _as_image(image)
         w, h = img.dimensions
         cent = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, 4)
-        out = np.empty((h, w, 4), np.uint8)
+        out = _out_image(out, h, w)
         _native.check(self._lib.kmg_remap(self._ctx, _ptr(img.rgba), w, h, cent.ctypes.data_as(C.POINTER(C.c_float)),
                                           cent.shape[0], int(color_space), int(reduce_mode), _ptr(out)))
         return Image((w, h), out)
@@ -261,11 +287,16 @@ class ImageProcessor:
         return Image((ow, oh), out)
 
     def reduce_batch(self, color_count: int, frames: np.ndarray, reduce_mode: ReduceMode = ReduceMode.Replace,
-                     opts: Opts | None = None, color_space: ColorSpace = ColorSpace.Lab):
-        """Batch of equally sized frames, array (n, h, w, 4)."""
+                     opts: Opts | None = None, color_space: ColorSpace = ColorSpace.Lab,
+                     out: np.ndarray | None = None):
+        """Batch of equally sized frames, array (n, h, w, 4).  Chunks of frames are pipelined
+        (upload / kernels / read-back overlap) when `frames` and `out` are page-locked (pinned_empty)."""
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         n, h, w, _ = frames.shape
-        out = np.empty_like(frames)
+        if out is None:
+            out = np.empty_like(frames)
+        elif out.dtype != np.uint8 or out.shape != frames.shape or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a contiguous uint8 array shaped like frames")
         cent = np.empty((n, int(color_count), 4), np.float32)
         passes = np.zeros(n, np.uint32)
         o = (opts or Opts()).to_c()
