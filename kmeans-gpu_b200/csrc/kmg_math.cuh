@@ -53,26 +53,36 @@ __device__ __forceinline__ float srgb_decode100(uint32_t v) {
   float r = (c > 0.04045f) ? pow_f32(fdiv(fadd(c, 0.055f), 1.055f), 2.4f) : fdiv(c, 12.92f);
   return fmul(r, 100.0f);
 }
-// pow_f32(t, 1.0f / 3.0f) for 2^-10 < t < 2^4 without the ~200 FP64 instructions of pow():
-// one Newton step of the cube root in double from a MUFU seed (relative error <= ~3e-13), times
-// t^(e - 1/3) for the f32 exponent e = 0.3333333432674408 (= 1 + (e - 1/3) ln t to 1e-15), rounded
-// to f32.  Ziv's test: when the double lies within 2e-12 (relative) of an f32 rounding boundary,
-// or the result is a power of two, the full pow() decides — so the value returned is always the
-// one pow_f32 returns (checked over all 2^24 colours by test_convert_lab_all_16m_colours).
+// pow_f32(t, 1.0f / 3.0f) for 2^-10 < t < 2^4 without the ~200 FP64 instructions of pow() and
+// without any f32<->f64 conversion (those run on the quarter-rate XU pipe): one Newton step of
+// the cube root from a MUFU seed y0, carried as an unevaluated sum y0 + lo of two floats.
+//   y0^3 - t  is formed exactly with FMA error-free products  (y0^2 = p + e1, p*y0 = q + e2,
+//             q - t exact by Sterbenz), its f32 rounding is ~6e-14 t
+//   lo        = -(y0^3 - t) * r + y0 * c,  r ~ 1/(3 y0^2),  c = (e - 1/3) ln t for the f32 exponent
+//             e = 0.3333333432674408;  y0 + lo = t^e (1 + ~4e-13)
+//   f         = RN(y0 + lo) — ONE rounding of the exact sum of two floats; rem = lo - (f - y0) is
+//             its exact residual (Fast2Sum)
+// Ziv's test: when y0 + lo lies within 2e-12 f of an f32 rounding boundary (|rem| close to half an
+// ulp), or f is a power of two, the full pow() decides — so the value returned is always the one
+// pow_f32 returns (checked over all 2^24 colours by test_convert_lab_all_16m_colours).
 __device__ __noinline__ float pow_third_slow(float t) { return pow_f32(t, 1.0f / 3.0f); }
 __device__ __forceinline__ float pow_third(float t) {
   float lg, y0, r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(lg * 0.33333334f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(3.0f * y0 * y0));
-  const double y0d = (double)y0;
-  const double res = fma(y0d * y0d, y0d, -(double)t);
-  const double y1 = fma(-res, (double)r, y0d);
-  const double yd = y1 * fma(6.885803302144935e-9, (double)lg, 1.0);  // (e - 1/3) * ln 2 * log2 t
-  const float f = __double2float_rn(yd);
-  const double h = (double)__int_as_float((__float_as_int(f) & 0x7f800000) - (24 << 23));  // half an ulp of f
-  const double gap = fabs(fabs(yd - (double)f) - h);
-  if (gap < 2.0e-12 * yd || (__float_as_int(f) & 0x007fffff) == 0) return pow_third_slow(t);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__fmul_rn(lg, 0.33333334f)));
+  const float p = __fmul_rn(y0, y0);
+  const float e1 = __fmaf_rn(y0, y0, -p);
+  const float q = __fmul_rn(p, y0);
+  const float e2 = __fmaf_rn(p, y0, -q);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(3.0f, p)));
+  const float res = __fadd_rn(__fsub_rn(q, t), __fmaf_rn(e1, y0, e2));
+  const float c = __fmul_rn(6.8858033e-9f, lg);  // (e - 1/3) * ln 2 * log2 t
+  const float lo = __fmaf_rn(y0, c, -__fmul_rn(res, r));
+  const float f = __fadd_rn(y0, lo);
+  const float rem = __fsub_rn(lo, __fsub_rn(f, y0));
+  const float h = __int_as_float((__float_as_int(f) & 0x7f800000) - (24 << 23));  // half an ulp of f
+  const float gap = fabsf(__fsub_rn(fabsf(rem), h));
+  if (gap < __fmul_rn(2.0e-12f, f) || (__float_as_int(f) & 0x007fffff) == 0) return pow_third_slow(t);
   return f;
 }
 
