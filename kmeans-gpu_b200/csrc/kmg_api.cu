@@ -170,6 +170,7 @@ struct kmg_ctx {
   // and whether clusters of 8 / 16 CTAs can be scheduled
   size_t small_dyn[3] = {0, 0, 0};
   bool small_cluster_ok[3][2] = {{false, false}, {false, false}, {false, false}};
+  int small_occ1[3] = {0, 0, 0};  // resident CTAs per SM in throughput mode (no planes in shared memory)
   // multi-GPU
   int n_ranks = 1, rank = 0;
 #if KMG_HAVE_NCCL_HEADER
@@ -278,6 +279,10 @@ struct SmallPlan {
   int variant = -1;          // 0: <8,512>, 1: <16,512>, 2: <32,256>
   unsigned int kcap = 0, threads = 0, csize = 0, ppc = 0;
   size_t smem = 0;
+  // throughput mode (large batches): csize 1, `grid` persistent CTAs, planes in `scratch` bytes of HBM/L2
+  bool throughput = false;
+  unsigned int grid = 0;
+  size_t scratch = 0;
 };
 static const void* small_fn(int variant) {
   return variant == 0 ? (const void*)SMALL8 : variant == 1 ? (const void*)SMALL16 : (const void*)SMALL32;
@@ -301,6 +306,14 @@ static void small_probe(kmg_ctx* ctx, const cudaDeviceProp& prop) {
       continue;
     }
     ctx->small_dyn[v] = dyn;
+    {
+      int occ = 0;
+      const size_t smem1 = small_smem_bytes(0, SMALL_KCAP[v], SMALL_THREADS[v], 1);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)SMALL_THREADS[v], smem1) == cudaSuccess)
+        ctx->small_occ1[v] = occ;
+      else
+        cudaGetLastError();
+    }
     for (int c = 0; c < 2; ++c) {
       const unsigned int csize = c == 0 ? 8u : 16u;
       cudaLaunchConfig_t cfg{};
@@ -329,6 +342,20 @@ static bool small_plan(kmg_ctx* ctx, unsigned long long n, uint32_t k, uint32_t 
   if (k > 32 || n == 0 || n > (1ull << 20)) return false;
   const int v = k <= 8 ? 0 : (k <= 16 ? 1 : 2);
   if (ctx->small_dyn[v] == 0) return false;
+  // A cluster finishes one image in ~0.15-0.25 ms but leaves its 8-16 SMs idle during barriers; a
+  // lone CTA needs ~1 ms per image and keeps its SM busy.  From ~40 frames on the lone CTAs win.
+  if (n_frames >= 40 && ctx->small_occ1[v] > 0 && n <= 65536) {
+    plan->variant = v;
+    plan->kcap = SMALL_KCAP[v];
+    plan->threads = SMALL_THREADS[v];
+    plan->csize = 1;
+    plan->ppc = (unsigned int)((n + 3) & ~3ull);
+    plan->smem = small_smem_bytes(0, SMALL_KCAP[v], SMALL_THREADS[v], 1);
+    plan->throughput = true;
+    plan->grid = (unsigned int)std::min<unsigned long long>(n_frames, (unsigned long long)ctx->sms * ctx->small_occ1[v]);
+    plan->scratch = (size_t)plan->grid * plan->ppc * 20;
+    return true;
+  }
   const int order_single[2] = {1, 0}, order_batch[2] = {0, 1};
   const int* order = n_frames > 1 ? order_batch : order_single;
   for (int o = 0; o < 2; ++o) {
@@ -352,7 +379,7 @@ static bool small_plan(kmg_ctx* ctx, unsigned long long n, uint32_t k, uint32_t 
 static int launch_small(kmg_ctx* ctx, const SmallPlan& plan, const SmallParams& prm, const JobPtrs& J0, uint32_t n_frames,
                         cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(plan.csize * n_frames);
+  cfg.gridDim = dim3(plan.throughput ? plan.grid : plan.csize * n_frames);
   cfg.blockDim = dim3(plan.threads);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = s;
@@ -1007,7 +1034,7 @@ static int resolve_seed(const kmg_opts& o, uint32_t gw, uint32_t gh, unsigned lo
 // and RGBA8 palette in every blob.  Asynchronous on s.
 static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uint8_t* d_rgba, uint32_t n_frames,
                                   uint32_t w, uint32_t h, uint32_t iw, uint32_t ih, uint32_t k, int cs, const kmg_opts& o,
-                                  void* blob, size_t blob_stride, int tail, kmg_job* job, cudaStream_t s) {
+                                  void* blob, size_t blob_stride, int tail, void* scratch, kmg_job* job, cudaStream_t s) {
   unsigned long long seed = 0;
   TRY(resolve_seed(o, iw, ih, &seed));
   job->ctx = ctx;
@@ -1037,6 +1064,9 @@ static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uin
   prm.tail = tail;
   prm.blob_stride = blob_stride;
   prm.lut = ctx->d_lut;
+  prm.gscratch = plan.throughput ? (unsigned char*)scratch : nullptr;
+  prm.n_frames = n_frames;
+  if (plan.throughput && !scratch) return fail(KMG_ERR_BAD_ARG, "throughput plan without a scratch buffer");
   return launch_small(ctx, plan, prm, job->P, n_frames, s);
 }
 
@@ -1056,7 +1086,7 @@ static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, 
   SmallPlan plan;
   if (!(o.flags & KMG_OPT_NO_FUSED_KMEANS) && small_plan(ctx, n, k, 1, &plan)) {
     job->h_state = ws->h_state;
-    TRY(kmeans_small_on_device(ctx, plan, d_rgba, 1, w, h, iw, ih, k, cs, o, ws->blob.p, 0, tail, job, s));
+    TRY(kmeans_small_on_device(ctx, plan, d_rgba, 1, w, h, iw, ih, k, cs, o, ws->blob.p, 0, tail, nullptr, job, s));
     CU(cudaMemcpyAsync(ws->h_state, job->P.st, sizeof(JobState), cudaMemcpyDeviceToHost, s));
     if (prepared) *prepared = true;
     return KMG_OK;
@@ -1193,10 +1223,12 @@ static bool batch_plan(kmg_ctx* ctx, uint32_t w, uint32_t h, uint32_t k, uint32_
 // (frames on gridDim.y), strided read-back of centroids / pass counts.  Asynchronous on s.
 static int reduce_batch_fused(kmg_ctx* ctx, const SmallPlan& plan, const uint8_t* d_rgba, uint32_t n_frames, uint32_t w,
                               uint32_t h, uint32_t iw, uint32_t ih, uint32_t k, int cs, int mode, const kmg_opts& o,
-                              uint8_t* d_out, void* blobs, float* centroids_out, uint32_t* passes_out, cudaStream_t s) {
+                              uint8_t* d_out, void* blobs, void* scratch, float* centroids_out, uint32_t* passes_out,
+                              cudaStream_t s) {
   const size_t stride = batch_blob_stride(k);
   kmg_job job;
-  TRY(kmeans_small_on_device(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, o, blobs, stride, tail_for_mode(mode), &job, s));
+  TRY(kmeans_small_on_device(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, o, blobs, stride, tail_for_mode(mode), scratch,
+                             &job, s));
   TRY(launch_remap(&job, d_rgba, w, h, mode, d_out, s, true, n_frames, stride));
   if (centroids_out)
     CU(cudaMemcpy2DAsync(centroids_out, (size_t)k * 16, job.P.cent, stride, (size_t)k * 16, n_frames, cudaMemcpyDeviceToHost, s));
@@ -1223,8 +1255,9 @@ extern "C" int kmg_dev_reduce_batch(kmg_ctx* ctx, const uint8_t* d_rgba, uint32_
     // the frames were produced on the caller's stream: stay on it
     cudaStream_t s = pick_stream(ctx, stream);
     TRY(ws->blob.ensure((size_t)n_frames * batch_blob_stride(k)));
-    TRY(reduce_batch_fused(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, mode, o, d_out, ws->blob.p, centroids_out,
-                           passes_out, s));
+    if (plan.throughput) TRY(ws->work.ensure(plan.scratch));
+    TRY(reduce_batch_fused(ctx, plan, d_rgba, n_frames, w, h, iw, ih, k, cs, mode, o, d_out, ws->blob.p, ws->work.p,
+                           centroids_out, passes_out, s));
     CU(cudaStreamSynchronize(s));
     return KMG_OK;
   }
@@ -1286,10 +1319,13 @@ extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_fr
       TRY(ws->in.ensure((size_t)nf * frame_bytes));
       TRY(ws->out.ensure((size_t)nf * frame_bytes));
       TRY(ws->blob.ensure((size_t)nf * stride));
+      SmallPlan cplan;  // a chunk is a small batch: clusters unless it is large enough for the throughput mode
+      if (!small_plan(ctx, (unsigned long long)iw * ih, k, nf, &cplan)) return fail(KMG_ERR_CUDA, "no launch plan for a chunk");
+      if (cplan.throughput) TRY(ws->work.ensure(cplan.scratch));
       cudaStream_t s = ws->stream;
       CU(cudaMemcpyAsync(ws->in.p, rgba + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, s));
-      TRY(reduce_batch_fused(ctx, plan, (const uint8_t*)ws->in.p, nf, w, h, iw, ih, k, cs, mode, o, (uint8_t*)ws->out.p,
-                             ws->blob.p, centroids_out ? centroids_out + (size_t)f0 * k * 4 : nullptr,
+      TRY(reduce_batch_fused(ctx, cplan, (const uint8_t*)ws->in.p, nf, w, h, iw, ih, k, cs, mode, o, (uint8_t*)ws->out.p,
+                             ws->blob.p, ws->work.p, centroids_out ? centroids_out + (size_t)f0 * k * 4 : nullptr,
                              passes_out ? passes_out + f0 : nullptr, s));
       CU(cudaMemcpyAsync(out_rgba + (size_t)f0 * frame_bytes, ws->out.p, (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, s));
     }

@@ -14,7 +14,10 @@
 //     integer accumulators, a block fold, an all-to-all of the k x 4 int64 partial sums through
 //     DSMEM, one cluster barrier, and a redundant, fixed-order finalisation in every CTA — so all
 //     CTAs hold identical centroids and take the same stop decision without further traffic.
-// A batch of frames is one launch with one cluster per frame (BASELINE config 5).
+// A batch of frames is one launch with one cluster per frame (BASELINE config 5).  Large batches
+// switch to a throughput mode of the same code: cluster size 1, one persistent CTA per SM looping
+// over frames, the two planes in an L2-resident scratch slice — a cluster finishes one image sooner
+// but idles its SMs during barriers and the serial finalisation, a lone CTA keeps its SM busy.
 //
 // Results are bit-identical to the multi-launch path (k_resize, k_convert, k_init_round, k_lloyd):
 // every value that is stored or compared is computed by the same ex:: arithmetic, and the centroid
@@ -58,6 +61,11 @@ struct SmallParams {
   int tail;                      // 0: centroids only, 1: + search table and RGBA8 palette, 2: + dither threshold
   size_t blob_stride;            // bytes between the job blobs of consecutive frames
   const float* lut;
+  // Throughput mode for large batches: one persistent CTA per SM (no cluster) walks the frames
+  // blockIdx.x, blockIdx.x + gridDim.x, ...; its work / distance planes live in a per-CTA slice of
+  // this L2-resident scratch (ppc * 20 bytes each) instead of shared memory.  NULL: cluster mode.
+  unsigned char* gscratch;
+  unsigned int n_frames;
 };
 
 // exchange slots per rank: k x 4 sums + {exact-path pixel count, pad}
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int csize = cluster.num_blocks();
   const unsigned int rank = cluster.block_rank();
-  const unsigned int frame = blockIdx.x / csize;
+  const bool gmode = prm.gscratch != nullptr;
   const unsigned int tid = threadIdx.x;
   const unsigned int lane = tid & 31u, warp = tid >> 5;
   const unsigned int k = prm.k;
@@ -102,10 +110,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   const unsigned int XS = small_xslots(KCAP);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_work = reinterpret_cast<float4*>(smem_raw);
-  float* s_dmin = reinterpret_cast<float*>(smem_raw + (size_t)ppc * 16);
-  int4* s_acc = reinterpret_cast<int4*>(smem_raw + (size_t)ppc * 20);
-  long long* s_x = reinterpret_cast<long long*>(smem_raw + (size_t)ppc * 20 + (size_t)KCAP * THREADS * 16);
+  unsigned char* plane_base = gmode ? prm.gscratch + (size_t)blockIdx.x * ((size_t)ppc * 20) : smem_raw;
+  unsigned char* rest = gmode ? smem_raw : smem_raw + (size_t)ppc * 20;
+  float4* s_work = reinterpret_cast<float4*>(plane_base);
+  float* s_dmin = reinterpret_cast<float*>(plane_base + (size_t)ppc * 16);
+  int4* s_acc = reinterpret_cast<int4*>(rest);
+  long long* s_x = reinterpret_cast<long long*>(rest + (size_t)KCAP * THREADS * 16);
   // every warp searches its own copy of the table (built redundantly from the shared centroids)
   __shared__ __align__(16) unsigned char s_tab_raw[NW][TAB_BYTES];
   __shared__ float4 s_cent[KCAP];
@@ -119,19 +129,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   __shared__ unsigned int s_slow;
   CentRec* s_tab = reinterpret_cast<CentRec*>(s_tab_raw[warp]);
 
-  const JobPtrs J = job_at(J0, (size_t)frame * prm.blob_stride);
-  const uint32_t* src = prm.src + (size_t)frame * prm.frame_px;
   const unsigned int N = prm.dw * prm.dh;
   const unsigned int first = rank * ppc;
   const unsigned int n_local = first < N ? min(ppc, N - first) : 0u;
-
-  KMG_TRACE_DECL;
-  KMG_TRACE_MARK();  // 0: start
-  // ---- shrink + convert into the local slice of the work plane --------------------------------
   for (unsigned int c = tid; c < 256; c += THREADS) {
     s_lut[c] = prm.lut[c];
     s_u8f[c] = fdiv((float)c, 255.0f);
   }
+
+  // cluster mode: exactly one frame per cluster; throughput mode: this CTA's share of the batch
+  const unsigned int frame_step = gmode ? gridDim.x : 0xffffffffu;
+  for (unsigned int frame = gmode ? blockIdx.x : blockIdx.x / csize; frame < prm.n_frames;
+       frame = frame_step > prm.n_frames - frame ? prm.n_frames : frame + frame_step) {
+  const JobPtrs J = job_at(J0, (size_t)frame * prm.blob_stride);
+  const uint32_t* src = prm.src + (size_t)frame * prm.frame_px;
+
+  KMG_TRACE_DECL;
+  KMG_TRACE_MARK();  // 0: start
+  // ---- shrink + convert into the local slice of the work plane --------------------------------
   if (tid < KCAP) s_flag[tid] = 0;
   if (tid == 0) s_slow = 0;
   __syncthreads();
@@ -152,16 +167,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
         for (int u = 0; u < U; ++u) {
           const unsigned int i = min(i0 + u * THREADS, n_local - 1);
           t[u] = resize_taps(prm.sw, prm.sh, prm.dw, prm.dh, first + i);
-          tap[u][0] = __ldg(src + t[u].i00);
-          tap[u][1] = __ldg(src + t[u].i10);
-          tap[u][2] = __ldg(src + t[u].i01);
-          tap[u][3] = __ldg(src + t[u].i11);
+          tap[u][0] = __ldcs(src + t[u].i00);  // streaming: the source is read once
+          tap[u][1] = __ldcs(src + t[u].i10);
+          tap[u][2] = __ldcs(src + t[u].i01);
+          tap[u][3] = __ldcs(src + t[u].i11);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) v[u] = resize_blend(tap[u][0], tap[u][1], tap[u][2], tap[u][3], t[u].fx, t[u].fy, u8f);
       } else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = __ldg(src + first + min(i0 + u * THREADS, n_local - 1));
+        for (int u = 0; u < U; ++u) v[u] = __ldcs(src + first + min(i0 + u * THREADS, n_local - 1));
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
 
   // ---- farthest-point init (plus_plus_init.wgsl, kmeans++_calc_diff.wgsl) ----------------------
   auto pixel_colour = [&](unsigned int g) -> float4 {  // any pixel of the image, through DSMEM
-    const float4* owner = cluster.map_shared_rank(s_work, g / ppc);
+    const float4* owner = gmode ? s_work : cluster.map_shared_rank(s_work, g / ppc);
     float4 v = owner[g % ppc];
     v.w = 1.0f;
     return v;
@@ -189,13 +204,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
   for (unsigned int j = 1; j < k; ++j) {
     const float cc = ex::chroma(c.y, c.z);
     unsigned long long best = 0ull;
-    for (unsigned int i = tid; i < n_local; i += THREADS) {
-      const float4 v = s_work[i];
-      const float d = ex::cie94_c(v.x, v.y, v.z, v.w, c.x, c.y, c.z, cc);
-      const float dm = j == 1 ? fminf(1000000.0f, d) : fminf(s_dmin[i], d);  // kmeans++_calc_diff.wgsl:27-31
-      s_dmin[i] = dm;
-      const unsigned long long key = ((unsigned long long)__float_as_uint(dm) << 32) | (unsigned long long)((first + i) ^ 15u);
-      best = key > best ? key : best;
+    constexpr int UI = 4;  // pixels in flight per thread (the planes may sit in L2)
+    for (unsigned int i0 = tid; i0 < n_local; i0 += UI * THREADS) {
+      float4 v[UI];
+      float prev[UI];
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const unsigned int i = i0 + u * THREADS;
+        const bool ok = i < n_local;
+        v[u] = ok ? s_work[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        prev[u] = (ok && j > 1) ? s_dmin[i] : 1000000.0f;  // kmeans++_calc_diff.wgsl:27-31
+      }
+#pragma unroll
+      for (int u = 0; u < UI; ++u) {
+        const unsigned int i = i0 + u * THREADS;
+        if (i < n_local) {
+          const float d = ex::cie94_c(v[u].x, v[u].y, v[u].z, v[u].w, c.x, c.y, c.z, cc);
+          const float dm = fminf(prev[u], d);
+          s_dmin[i] = dm;
+          const unsigned long long key = ((unsigned long long)__float_as_uint(dm) << 32) | (unsigned long long)((first + i) ^ 15u);
+          best = key > best ? key : best;
+        }
+      }
     }
     best = warp_max_key(best);
     if (lane == 0) s_red[warp] = best;
@@ -263,18 +293,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
 
     // assignment + thread-private accumulation over the local slice
     unsigned int slow = 0;
+    float4 nxt[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const unsigned int p = i * THREADS + tid;
+      nxt[i] = p < n_local ? s_work[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (unsigned int t = 0; t < tiles; ++t) {
       Pix<P> px;
       bool valid[P];
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        const unsigned int p = (t * P + i) * THREADS + tid;
-        valid[i] = p < n_local;
-        const float4 v = valid[i] ? s_work[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        px.L[i] = v.x;
-        px.a[i] = v.y;
-        px.b[i] = v.z;
-        px.C[i] = v.w;
+        valid[i] = (t * P + i) * THREADS + tid < n_local;
+        px.L[i] = nxt[i].x;
+        px.a[i] = nxt[i].y;
+        px.b[i] = nxt[i].z;
+        px.C[i] = nxt[i].w;
+      }
+      // the next tile's pixels are in flight while this one is searched (L2 latency in throughput mode)
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const unsigned int p = ((t + 1) * P + i) * THREADS + tid;
+        nxt[i] = p < n_local ? s_work[p] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       float eps[P];
       unsigned int idx[P];
@@ -483,6 +523,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
     }
   }
   KMG_TRACE_MARK();  // end
+  __syncthreads();  // throughput mode: the next frame reuses the shared state
+  }
 }
 
 }  // namespace kmg

@@ -424,6 +424,26 @@ def test_reduce_batch_device_and_host_pipeline(proc, D, K, oracle, torch, k, mod
     assert np.array_equal(want, host_out[5])
 
 
+@pytest.mark.parametrize("k,w,h,max_dim", [(16, 320, 180, 256), (8, 300, 200, 256), (24, 200, 256, 256), (5, 64, 48, 16)])
+def test_reduce_batch_throughput_mode(proc, D, K, oracle, torch, k, w, h, max_dim):
+    """Large batches run one persistent CTA per SM with the planes in an L2-resident scratch (>= 40
+    frames): same results as the cluster launch of a single image and as the oracle."""
+    n = 331  # more frames than SMs x resident CTAs: every CTA loops over several frames
+    frames = np.stack([oracle.synth(w * h, seed=5, blobs=2 * k, frame=f).reshape(h, w, 4) for f in range(n)])
+    opts = K.Opts(max_dim=max_dim)
+    out, cent, passes = D.reduce_batch(proc, dev_rgba(torch, frames), k, K.ReduceMode.Dither, opts=opts)
+    out = out.cpu().numpy()
+    for f in (0, 1, 147, 148, 149, 295, 296, n - 1):
+        single, c1, p1 = proc.reduce(k, frames[f], reduce_mode=K.ReduceMode.Dither, return_details=True, opts=opts)
+        assert p1 == passes[f], f
+        assert np.array_equal(bits(c1), bits(cent[f])), f
+        assert np.array_equal(single.rgba, out[f]), f
+    want, ocent, opasses = oracle.reduce(frames[200], k, "dither", opts=oracle.default_opts(sum_mode=1, max_dim=max_dim))
+    assert opasses == passes[200]
+    assert np.array_equal(bits(ocent), bits(cent[200]))
+    assert np.array_equal(want, out[200])
+
+
 def test_reduce_batch_many_chunks(proc, K, oracle):
     """More frames than one pipeline chunk holds (chunks of >= 16 frames through three workspaces)."""
     n, w, h = 70, 1920, 1080
