@@ -161,6 +161,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     proc = K.ImageProcessor(local)
+    comm_mode = 0
 
     n = W * H
     # rank r owns rows [r*H, (r+1)*H) of the 8192 x (8192*world) image
@@ -174,6 +175,7 @@ def run_ours(args):
             uid = torch.frombuffer(bytearray(D.comm_unique_id(proc)), dtype=torch.uint8).to(dev)
         dist.broadcast(uid, 0)
         D.comm_init(proc, bytes(uid.cpu().numpy().tobytes()), world, rank)
+        comm_mode = D.comm_mode(proc)
         job.set_shard(W, H * world, rank * H)
     job.init()
     torch.cuda.synchronize()
@@ -291,7 +293,9 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{W}x{H} blobs({BLOBS}) k={K_CLUSTERS} Lab assign+update iteration per GPU"
-                                   + (f", rows sharded over {world} GPUs with per-pass NCCL all-reduce of k x 4 int64 sums" if world > 1 else ""),
+                                   + (f", rows sharded over {world} GPUs, k x 4 int64 sums exchanged per pass "
+                                      + ("inside the pass kernel through peer-mapped mailboxes (NVLink)" if comm_mode == 2
+                                         else "by an NCCL all-reduce") if world > 1 else ""),
                        "k": K_CLUSTERS, "bytes_per_px": BYTES_PER_PX, "l2": "work plane 1 GiB per GPU > 126 MB L2",
                        "exact_path_pixels_per_pass": stats["slow_pixels"] / max(stats["passes"], 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -181,6 +181,10 @@ int kmg_job_get_sums(kmg_job* job, int64_t* sums_out, void* stream);
 int kmg_comm_unique_id(kmg_ctx* ctx, uint8_t id_out[128]);
 int kmg_comm_init(kmg_ctx* ctx, const uint8_t id[128], int n_ranks, int rank);
 int kmg_comm_destroy(kmg_ctx* ctx);
+/* How the per-pass sums of a sharded job travel: 0 = no communicator, 1 = NCCL all-reduce after the
+ * pass kernel, 2 = inside the pass kernel, through peer-mapped mailboxes over NVLink (chosen by
+ * kmg_comm_init when CUDA IPC peer mapping works between all ranks; at most 8 ranks). */
+int kmg_comm_mode(kmg_ctx* ctx);
 /* Marks the job as one shard of a distributed problem: global_w/global_h describe the whole image
  * and row_offset the first row of this shard (used by the init seed and tie rule). */
 int kmg_job_set_shard(kmg_job* job, uint32_t global_w, uint32_t global_h, uint32_t row_offset);

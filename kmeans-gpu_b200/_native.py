@@ -80,6 +80,7 @@ SIGNATURES = {
     "kmg_comm_unique_id": (C.c_int, [_vp, _u8p]),
     "kmg_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
     "kmg_comm_destroy": (C.c_int, [_vp]),
+    "kmg_comm_mode": (C.c_int, [_vp]),
     "kmg_job_set_shard": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "kmg_dev_remap": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _f32p, C.c_uint32, C.c_int, C.c_int, _vp, _vp]),
     "kmg_dev_remap_job": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_int, _vp, _vp]),

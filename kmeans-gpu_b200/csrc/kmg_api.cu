@@ -176,6 +176,11 @@ struct kmg_ctx {
 #if KMG_HAVE_NCCL_HEADER
   ncclComm_t comm = nullptr;
 #endif
+  // peer mailboxes for the in-kernel exchange of the per-pass sums (PeerXchg); p2p == false: NCCL all-reduce
+  bool p2p = false;
+  void* mbox_own = nullptr;                // this GPU's mailbox (cudaMalloc, exported through CUDA IPC)
+  void* mbox_peer[MAX_PEERS] = {nullptr};  // every rank's mailbox as mapped here (own entry = mbox_own)
+  uint32_t xchg_seq = 0x1234567u;          // flag sequence base handed to the next sharded job
 };
 
 struct kmg_job {
@@ -195,7 +200,13 @@ struct kmg_job {
   bool sharded = false;
   uint32_t global_w = 0, global_h = 0, row_offset = 0;
   float* d_xfer = nullptr;  // 4 floats, colour broadcast during distributed init
+  uint32_t xchg_base = 0;   // PeerXchg::seq_base of this job
 };
+
+#if KMG_HAVE_NCCL_HEADER
+static int p2p_setup(kmg_ctx* ctx);
+static void p2p_teardown(kmg_ctx* ctx);
+#endif
 
 // Accumulator copies: the thread-private kernels (k <= 32) flush rarely, 8 copies are plenty; the
 // global-reduction kernel adds 4 values per pixel, so every resident block gets its own copy
@@ -480,7 +491,10 @@ extern "C" void kmg_destroy(kmg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
 #if KMG_HAVE_NCCL_HEADER
-  if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+  if (ctx->comm) {
+    p2p_teardown(ctx);
+    nccl_api().CommDestroy(ctx->comm);
+  }
 #endif
   for (Workspace* w : ctx->pool) {
     w->release();
@@ -549,28 +563,51 @@ static int launch_prepare(kmg_job* j, bool palette, cudaStream_t s) {
   return KMG_OK;
 }
 
+static constexpr unsigned int MBOX_XCAP = MAX_K * 4;  // int64 slots per (parity, rank)
+static constexpr size_t MBOX_DATA_BYTES = (size_t)2 * MAX_PEERS * MBOX_XCAP * 8;
+static constexpr size_t MBOX_BYTES = MBOX_DATA_BYTES + (size_t)2 * MAX_PEERS * 4;
+
+static PeerXchg peer_xchg(const kmg_ctx* ctx, const kmg_job* j, bool fused) {
+  PeerXchg X;
+  memset(&X, 0, sizeof(X));
+  if (fused) {
+    X.n_ranks = (unsigned int)ctx->n_ranks;
+    X.rank = (unsigned int)ctx->rank;
+    X.xcap = MBOX_XCAP;
+    X.seq_base = j->xchg_base;
+    for (int r = 0; r < ctx->n_ranks; ++r) {
+      X.mbox[r] = (long long*)ctx->mbox_peer[r];
+      X.flags[r] = (unsigned int*)((unsigned char*)ctx->mbox_peer[r] + MBOX_DATA_BYTES);
+    }
+  }
+  return X;
+}
+
 static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   kmg_ctx* ctx = j->ctx;
   const unsigned long long n = (unsigned long long)j->w * j->h;
-  const int partial = (j->sharded && ctx->n_ranks > 1) ? 1 : 0;
+  const bool dist = j->sharded && ctx->n_ranks > 1;
+  const bool fused = dist && ctx->p2p;
+  const int partial = dist ? (fused ? 2 : 1) : 0;
+  const PeerXchg X = peer_xchg(ctx, j, fused);
   if (j->k <= 8) {
     int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
-    LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X);
   } else if (j->k <= 16) {
     int grid = grid_for(ctx, n, 256 * 2, ctx->occ_private16);
-    LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial);
+    LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X);
   } else if (j->k <= 32) {
     int grid = grid_for(ctx, n, 128 * 4, ctx->occ_private32);
-    LLOYD32<<<grid, 128, LLOYD32_SMEM, s>>>(j->P, j->work, n, j->color_space, partial);
+    LLOYD32<<<grid, 128, LLOYD32_SMEM, s>>>(j->P, j->work, n, j->color_space, partial, X);
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k));
     int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
-    LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial);
+    LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X);
   }
   LAUNCHED(ctx);
   CHECK_LAUNCH();
 #if KMG_HAVE_NCCL_HEADER
-  if (partial) {
+  if (partial == 1) {
     NC(nccl_api().AllReduce(j->P.acc, j->P.acc, (size_t)j->k * 4, ncclInt64, ncclSum, ctx->comm, s));
     k_finalize<<<1, 256, 0, s>>>(j->P, j->color_space);
     LAUNCHED(ctx);
@@ -690,6 +727,8 @@ static int job_setup(kmg_job* j, kmg_ctx* ctx, const float* d_work, uint32_t w, 
 static int job_read_state(kmg_job* j, cudaStream_t s) {
   CU(cudaMemcpyAsync(j->h_state, j->P.st, sizeof(JobState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  if (j->h_state->conv == PASS_FAULT)
+    return fail(KMG_ERR_NCCL, "a peer GPU did not deliver its partial sums within 4 s (pass %u)", j->h_state->passes);
   return KMG_OK;
 }
 
@@ -837,6 +876,9 @@ extern "C" int kmg_job_set_shard(kmg_job* j, uint32_t gw, uint32_t gh, uint32_t 
     return fail(KMG_ERR_BAD_ARG, "shard rows [%u,%u) of width %u do not fit the %ux%u image", row_offset,
                 row_offset + j->h, j->w, gw, gh);
   j->sharded = true;
+  // every rank creates its sharded jobs in the same order, so the bases agree across ranks
+  j->xchg_base = j->ctx->xchg_seq;
+  j->ctx->xchg_seq += 0x9E3779B1u;
   j->global_w = gw;
   j->global_h = gh;
   j->row_offset = row_offset;
@@ -1344,6 +1386,89 @@ extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_fr
 // ------------------------------------------------------------------------------------------------
 // multi-GPU communicator
 
+#if KMG_HAVE_NCCL_HEADER
+// Peer mailboxes for the in-kernel exchange: every rank exports its mailbox through CUDA IPC, the
+// 64-byte handles travel over the freshly created NCCL communicator, and every rank maps all the
+// others.  Any failure (no peer access, IPC unavailable in this container, > 8 ranks) leaves
+// p2p == false on ALL ranks and the per-pass NCCL all-reduce stays in use.
+static void p2p_teardown(kmg_ctx* ctx) {
+  for (unsigned int r = 0; r < MAX_PEERS; ++r) {
+    if (ctx->mbox_peer[r] && ctx->mbox_peer[r] != ctx->mbox_own) cudaIpcCloseMemHandle(ctx->mbox_peer[r]);
+    ctx->mbox_peer[r] = nullptr;
+  }
+  if (ctx->mbox_own) cudaFree(ctx->mbox_own);
+  ctx->mbox_own = nullptr;
+  ctx->p2p = false;
+  cudaGetLastError();
+}
+
+static int p2p_setup(kmg_ctx* ctx) {
+  ctx->p2p = false;
+  if (ctx->n_ranks < 2) return KMG_OK;
+  cudaStream_t s = ctx->stream;
+  const int n = ctx->n_ranks;
+  int ok = (n <= (int)MAX_PEERS && !getenv("KMG_NO_P2P")) ? 1 : 0;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc(&ctx->mbox_own, MBOX_BYTES) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(ctx->mbox_own, 0, MBOX_BYTES, s) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, ctx->mbox_own) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // all-gather {ok, handle} (device staging buffers; 128 bytes per rank)
+  const size_t rec = 128;
+  unsigned char *d_send = nullptr, *d_recv = nullptr;
+  CU(cudaMalloc((void**)&d_send, rec));
+  CU(cudaMalloc((void**)&d_recv, rec * n));
+  std::vector<unsigned char> h_send(rec, 0), h_recv(rec * n, 0);
+  h_send[0] = (unsigned char)ok;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle fits the record");
+  memcpy(h_send.data() + 64, &mine, sizeof(mine));
+  CU(cudaMemcpyAsync(d_send, h_send.data(), rec, cudaMemcpyHostToDevice, s));
+  // one all-reduce-free gather: rank r contributes its record at offset r (sum of zero-padded byte vectors)
+  CU(cudaMemsetAsync(d_recv, 0, rec * n, s));
+  CU(cudaMemcpyAsync(d_recv + rec * ctx->rank, d_send, rec, cudaMemcpyDeviceToDevice, s));
+  NC(nccl_api().AllReduce(d_recv, d_recv, rec * n, ncclUint8, ncclSum, ctx->comm, s));
+  CU(cudaMemcpyAsync(h_recv.data(), d_recv, rec * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  int all_ok = 1;
+  for (int r = 0; r < n; ++r) all_ok &= h_recv[rec * r] ? 1 : 0;
+  int mapped = all_ok;
+  if (all_ok) {
+    for (int r = 0; r < n && mapped; ++r) {
+      if (r == ctx->rank) {
+        ctx->mbox_peer[r] = ctx->mbox_own;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, h_recv.data() + rec * r + 64, sizeof(h));
+      if (cudaIpcOpenMemHandle(&ctx->mbox_peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->mbox_peer[r] = nullptr;
+        mapped = 0;
+      }
+    }
+  }
+  // second round: did every rank map every mailbox?
+  h_send.assign(rec, 0);
+  h_send[0] = (unsigned char)mapped;
+  CU(cudaMemcpyAsync(d_send, h_send.data(), rec, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_recv, 0, rec * n, s));
+  CU(cudaMemcpyAsync(d_recv + rec * ctx->rank, d_send, rec, cudaMemcpyDeviceToDevice, s));
+  NC(nccl_api().AllReduce(d_recv, d_recv, rec * n, ncclUint8, ncclSum, ctx->comm, s));
+  CU(cudaMemcpyAsync(h_recv.data(), d_recv, rec * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  int all_mapped = 1;
+  for (int r = 0; r < n; ++r) all_mapped &= h_recv[rec * r] ? 1 : 0;
+  if (all_mapped)
+    ctx->p2p = true;
+  else
+    p2p_teardown(ctx);
+  return KMG_OK;
+}
+#endif
+
 extern "C" int kmg_comm_unique_id(kmg_ctx* ctx, uint8_t id_out[128]) {
 #if KMG_HAVE_NCCL_HEADER
   if (!ctx || !id_out) return fail(KMG_ERR_BAD_ARG, "kmg_comm_unique_id: NULL argument");
@@ -1372,6 +1497,7 @@ extern "C" int kmg_comm_init(kmg_ctx* ctx, const uint8_t id_in[128], int n_ranks
   NC(nccl_api().CommInitRank(&ctx->comm, n_ranks, id, rank));
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
+  TRY(p2p_setup(ctx));
   return KMG_OK;
 #else
   (void)ctx;
@@ -1382,11 +1508,18 @@ extern "C" int kmg_comm_init(kmg_ctx* ctx, const uint8_t id_in[128], int n_ranks
 #endif
 }
 
+extern "C" int kmg_comm_mode(kmg_ctx* ctx) {
+  if (!ctx || ctx->n_ranks < 2) return 0;
+  return ctx->p2p ? 2 : 1;
+}
+
 extern "C" int kmg_comm_destroy(kmg_ctx* ctx) {
 #if KMG_HAVE_NCCL_HEADER
   if (!ctx) return fail(KMG_ERR_BAD_ARG, "kmg_comm_destroy: NULL ctx");
   if (ctx->comm) {
     CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    p2p_teardown(ctx);
     NC(nccl_api().CommDestroy(ctx->comm));
     ctx->comm = nullptr;
   }

@@ -58,6 +58,22 @@ struct JobPtrs {
 
 __host__ __device__ inline unsigned int pad32(unsigned int k) { return (k + 31u) & ~31u; }
 
+// Multi-GPU pixel sharding without a separate collective: the last block of a Lloyd pass on every
+// GPU stores its k x 4 partial sums straight into every peer's mailbox (peer-mapped memory, the
+// stores travel over NVLink / NVSwitch), raises a flag there, waits for the peers' flags in its
+// own mailbox and finalises — reduction and pass are one kernel.  Mailbox of a GPU:
+//   mbox  [2 parities][MAX_PEERS ranks][xcap] int64     flags [2 parities][MAX_PEERS ranks] u32
+constexpr unsigned int MAX_PEERS = 8;
+struct PeerXchg {
+  unsigned int n_ranks;  // 0: not in use
+  unsigned int rank;
+  unsigned int xcap;     // int64 slots per (parity, rank), >= 4 k
+  unsigned int seq_base; // flags carry seq_base + pass number + 1 (distinct per job)
+  long long* mbox[MAX_PEERS];      // rank r's mailbox as mapped on this GPU
+  unsigned int* flags[MAX_PEERS];
+};
+constexpr unsigned int PASS_FAULT = 0xffffffffu;  // JobState::conv when a peer did not answer
+
 // The job blob of frame f in a batch: every pointer shifted by f * blob_stride bytes.
 __device__ __forceinline__ JobPtrs job_at(JobPtrs J, size_t off) {
   JobPtrs R;
@@ -653,27 +669,89 @@ __global__ void k_init_pick(JobPtrs J, const float4* __restrict__ work, unsigned
 // the image.  The last block to finish turns the sums into the new centroids, convergence flags
 // and the next table, so a pass is exactly one launch and needs no host round trip.
 
+// mode 0: single GPU.  mode 1: leave the folded partial sums in accumulator copy 0 for an external
+// all-reduce (k_finalize completes the pass).  mode 2: exchange them with the peers right here.
 template <int THREADS>
-__device__ void finalize_pass(const JobPtrs& J, int color_space, bool distributed_partial) {
+__device__ void finalize_pass(const JobPtrs& J, int color_space, int mode, const PeerXchg& X) {
   JobState* st = J.st;
   const unsigned int k = st->k;
   const unsigned int tid = threadIdx.x;
   __shared__ unsigned int s_conv;
-  if (tid == 0) s_conv = 0;
+  __shared__ unsigned int s_fault;
+  if (tid == 0) {
+    s_conv = 0;
+    s_fault = 0;
+  }
   __syncthreads();
+  const unsigned int par = st->passes & 1u;
+  const unsigned int seq = X.seq_base + st->passes + 1u;
+  if (mode == 2) {
+    // fold the local copies and post them to every rank (own mailbox included)
+    for (unsigned int c = tid; c < k; c += THREADS) {
+      long long s[4] = {0, 0, 0, 0};
+      for (unsigned int copy = 0; copy < J.acc_copies; ++copy) {
+        long long* a = J.acc + ((size_t)copy * k + c) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          s[q] += __ldcg(a + q);
+          a[q] = 0;
+        }
+      }
+      const size_t slot = ((size_t)par * MAX_PEERS + X.rank) * X.xcap + (size_t)c * 4;
+      for (unsigned int r = 0; r < X.n_ranks; ++r) {
+        longlong2* dst = reinterpret_cast<longlong2*>(X.mbox[r] + slot);
+        dst[0] = make_longlong2(s[0], s[1]);
+        dst[1] = make_longlong2(s[2], s[3]);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < X.n_ranks) {
+      volatile unsigned int* theirs = X.flags[tid] + par * MAX_PEERS + X.rank;
+      *theirs = seq;
+      volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + tid;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*mine != seq) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {  // 4 s: a peer never launched this pass
+          s_fault = 1;
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (s_fault) {
+      if (tid == 0) {
+        st->conv = PASS_FAULT;
+        st->done = 1;
+        st->ticket = 0;
+      }
+      return;
+    }
+  }
   unsigned int conv = 0;
   for (unsigned int c = tid; c < k; c += THREADS) {
     long long s[4] = {0, 0, 0, 0};
-    for (unsigned int copy = 0; copy < J.acc_copies; ++copy) {
-      long long* a = J.acc + ((size_t)copy * k + c) * 4;
+    if (mode == 2) {
+      for (unsigned int r = 0; r < X.n_ranks; ++r) {  // fixed rank order on every GPU
+        const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap + (size_t)c * 4;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        s[q] += __ldcg(a + q);
-        if (!distributed_partial || copy > 0) a[q] = 0;
+        for (int q = 0; q < 4; ++q) s[q] += a[q];
+      }
+    } else {
+      for (unsigned int copy = 0; copy < J.acc_copies; ++copy) {
+        long long* a = J.acc + ((size_t)copy * k + c) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          s[q] += __ldcg(a + q);
+          if (mode == 0 || copy > 0) a[q] = 0;
+        }
       }
     }
-    if (distributed_partial) {
-      // multi-GPU: leave the folded partial in copy 0 for the all-reduce; k_finalize completes it
+    if (mode == 1) {
+      // leave the folded partial in copy 0 for the all-reduce; k_finalize completes it
       long long* a0 = J.acc + (size_t)c * 4;
 #pragma unroll
       for (int q = 0; q < 4; ++q) a0[q] = s[q];
@@ -693,7 +771,7 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, bool distribute
       conv += (ex::cie94(nc.x, nc.y, nc.z, prev.x, prev.y, prev.z) < st->conv_threshold) ? 1u : 0u;
     }
   }
-  if (distributed_partial) {
+  if (mode == 1) {
     __syncthreads();
     if (tid == 0) st->ticket = 0;
     return;
@@ -716,7 +794,12 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, bool distribute
 // Finalise after an external all-reduce of acc copy 0 (multi-GPU).
 __global__ void __launch_bounds__(256) k_finalize(JobPtrs J, int color_space) {
   if (J.st->done) return;
-  finalize_pass<256>(J, color_space, false);
+  PeerXchg none;
+  none.n_ranks = 0;
+  none.rank = 0;
+  none.xcap = 0;
+  none.seq_base = 0;
+  finalize_pass<256>(J, color_space, 0, none);
 }
 
 template <int THREADS, int P, bool CHECK>
@@ -796,7 +879,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
 template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4* __restrict__ work,
                                                          unsigned long long n, int color_space,
-                                                         int distributed_partial) {
+                                                         int distributed_mode, PeerXchg X) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(16) unsigned char s_tab_static[KT > 0 ? (KT / 8) * CHUNK_BYTES : 16];
   __shared__ bool s_last;
@@ -875,7 +958,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
   __syncthreads();
   if (s_last) {
     __threadfence();
-    finalize_pass<THREADS>(J, color_space, distributed_partial != 0);
+    finalize_pass<THREADS>(J, color_space, distributed_mode, X);
   }
 }
 
@@ -933,8 +1016,13 @@ __global__ void __launch_bounds__(THREADS) k_assign(JobPtrs J, const float4* __r
 // the near-tied candidates with reference arithmetic.  The output colour of cluster c is the
 // pre-reverted palette entry pal[c] (swap.wgsl:22-24 + lab_to_rgb.wgsl of a constant).
 // mix_colors.wgsl:14-17
-__device__ __constant__ float c_bayer[16] = {0.f, 8.f, 2.f, 10.f, 12.f, 4.f, 14.f, 6.f,
-                                             3.f, 11.f, 1.f, 9.f, 15.f, 7.f, 13.f, 5.f};
+constexpr unsigned long long bayer_nibbles() {
+  const unsigned long long m[16] = {0, 8, 2, 10, 12, 4, 14, 6, 3, 11, 1, 9, 15, 7, 13, 5};
+  unsigned long long v = 0;
+  for (int j = 0; j < 16; ++j) v |= m[j] << (4 * j);
+  return v;
+}
+constexpr unsigned long long BAYER_NIBBLES = bayer_nibbles();
 
 // Exact pixel of the remap kernels: Lab through the FP64 pow path (+ the dither offset).
 template <int MODE>
@@ -1031,7 +1119,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t
           xi -= w;
           ++yi;
         }
-        float iv = c_bayer[(xi & 3u) + ((yi & 3u) << 2)] * 0.0625f - 0.5f;  // mix_colors.wgsl:21-27,70
+        // index_matrix[x % 4 + 4 * (y % 4)] / 16 - 0.5 (mix_colors.wgsl:14-17,21-27,70); the sixteen
+        // 4-bit entries sit in one 64-bit constant (no divergent constant-bank load)
+        const unsigned int cell = (xi & 3u) + ((yi & 3u) << 2);
+        float iv = (float)((unsigned int)(BAYER_NIBBLES >> (4u * cell)) & 15u) * 0.0625f - 0.5f;
         off[i] = fmul(thr, iv);
         L += off[i];
         a += off[i];

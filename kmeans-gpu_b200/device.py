@@ -189,5 +189,10 @@ def comm_init(proc: ImageProcessor, uid: bytes, n_ranks: int, rank: int):
     _native.check(proc._lib.kmg_comm_init(proc.ctx, buf, n_ranks, rank))
 
 
+def comm_mode(proc: ImageProcessor) -> int:
+    """0: none, 1: NCCL all-reduce per pass, 2: in-kernel exchange through peer-mapped mailboxes."""
+    return int(proc._lib.kmg_comm_mode(proc.ctx))
+
+
 def comm_destroy(proc: ImageProcessor):
     _native.check(proc._lib.kmg_comm_destroy(proc.ctx))
