@@ -32,6 +32,7 @@ using namespace kmg;
 // Lloyd-pass variants: <table length (0 = runtime), accumulator capacity, threads, pixels/thread,
 // thread-private accumulators, min blocks/SM>
 #define LLOYD8 k_lloyd<8, 8, 256, 4, true, 2>
+#define LLOYD8C k_lloyd<8, 8, 256, 4, true, 2, true>
 #define LLOYD16 k_lloyd<16, 16, 256, 2, true, 2>
 #define LLOYD32 k_lloyd<0, 32, 128, 4, true, 3>
 #define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
@@ -181,6 +182,9 @@ struct kmg_ctx {
   void* mbox_own = nullptr;                // this GPU's mailbox (cudaMalloc, exported through CUDA IPC)
   void* mbox_peer[MAX_PEERS] = {nullptr};  // every rank's mailbox as mapped here (own entry = mbox_own)
   uint32_t xchg_seq = 0x1234567u;          // flag sequence base handed to the next sharded job
+  // constant-bank table slots (kmg_kernels.cuh: c_tab), handed to jobs with k <= 8
+  void* c_tab_dev = nullptr;  // nullptr: constant-bank tables switched off (KMG_NO_CONST_TABLE)
+  int occ_const8 = 1;
 };
 
 struct kmg_job {
@@ -201,7 +205,38 @@ struct kmg_job {
   uint32_t global_w = 0, global_h = 0, row_offset = 0;
   float* d_xfer = nullptr;  // 4 floats, colour broadcast during distributed init
   uint32_t xchg_base = 0;   // PeerXchg::seq_base of this job
+  // slot of the constant-bank table (k <= 8 passes), taken at the first pass, returned with the job
+  int cslot = -1;
+  bool cslot_tried = false;
+  ~kmg_job();
 };
+
+// The constant bank belongs to the device (one copy of the module per device), not to a context:
+// the free list is per device and process-wide.
+static std::mutex g_cslot_mu;
+static std::vector<int> g_cslots_free[64];
+static bool g_cslots_ready[64];
+static int cslot_acquire(kmg_ctx* ctx) {
+  if (!ctx->c_tab_dev || ctx->device >= 64) return -1;
+  std::lock_guard<std::mutex> g(g_cslot_mu);
+  std::vector<int>& fl = g_cslots_free[ctx->device];
+  if (!g_cslots_ready[ctx->device]) {
+    g_cslots_ready[ctx->device] = true;
+    for (int i = CTAB_SLOTS - 1; i >= 0; --i) fl.push_back(i);
+  }
+  if (fl.empty()) return -1;
+  int s = fl.back();
+  fl.pop_back();
+  return s;
+}
+// Jobs are only dropped after the work they enqueued has been waited for (every blocking entry
+// point synchronises; kmg_job_destroy frees device memory first, which synchronises the device).
+kmg_job::~kmg_job() {
+  if (cslot >= 0 && ctx) {
+    std::lock_guard<std::mutex> g(g_cslot_mu);
+    g_cslots_free[ctx->device].push_back(cslot);
+  }
+}
 
 #if KMG_HAVE_NCCL_HEADER
 static int p2p_setup(kmg_ctx* ctx);
@@ -479,6 +514,9 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
   small_probe(ctx, prop);
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, LLOYD8, 256, 8 * 256 * 16));
+  CU(cudaFuncSetAttribute(LLOYD8C, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_const8, LLOYD8C, 256, 8 * 256 * 16));
+  if (!getenv("KMG_NO_CONST_TABLE")) CU(cudaGetSymbolAddress(&ctx->c_tab_dev, c_tab));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, LLOYD16, 256, 16 * 256 * 16));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, LLOYD32, 128, LLOYD32_SMEM));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -591,18 +629,30 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   const int partial = dist ? (fused ? 2 : 1) : 0;
   const PeerXchg X = peer_xchg(ctx, j, fused);
   if (j->k <= 8) {
-    int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
-    LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X);
+    if (j->cslot < 0 && !j->cslot_tried) {
+      j->cslot_tried = true;
+      j->cslot = cslot_acquire(ctx);
+    }
+    if (j->cslot >= 0) {
+      // the table of this pass goes to the job's slot of the constant bank (see c_tab)
+      CU(cudaMemcpyAsync((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4, j->P.tab, 8 * sizeof(CentRec),
+                         cudaMemcpyDeviceToDevice, s));
+      int grid = grid_for(ctx, n, 256 * 4, ctx->occ_const8);
+      LLOYD8C<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X, j->cslot);
+    } else {
+      int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
+      LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
+    }
   } else if (j->k <= 16) {
     int grid = grid_for(ctx, n, 256 * 2, ctx->occ_private16);
-    LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X);
+    LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
   } else if (j->k <= 32) {
     int grid = grid_for(ctx, n, 128 * 4, ctx->occ_private32);
-    LLOYD32<<<grid, 128, LLOYD32_SMEM, s>>>(j->P, j->work, n, j->color_space, partial, X);
+    LLOYD32<<<grid, 128, LLOYD32_SMEM, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k));
     int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
-    LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X);
+    LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
   }
   LAUNCHED(ctx);
   CHECK_LAUNCH();

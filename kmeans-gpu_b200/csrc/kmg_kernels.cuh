@@ -102,6 +102,16 @@ __device__ __forceinline__ void tab_to_smem(CentRec* s_tab, const CentRec* __res
   for (unsigned int c = tid; c < kp; c += nthreads) *const_cast<CentRec*>(rec_at(s_tab, c)) = g_tab[c];
 }
 
+// Constant-bank copy of a small table (k <= 16), dense records, one slot per job in flight.  Values
+// read from the constant bank with a warp-uniform address live in *uniform* registers, and packed
+// FFMA2 takes a scalar-broadcast operand straight from a uniform register: the hot loop of a
+// small-k Lloyd pass then keeps no table in vector registers and issues no shared-memory loads for
+// it, which buys a third resident block per SM.  The host copies J.tab into the job's slot
+// (device-to-device, 24 k bytes) before each pass.
+constexpr int CTAB_SLOTS = 64;
+constexpr int CTAB_FLOATS = 16 * 6;
+__constant__ float c_tab[CTAB_SLOTS][CTAB_FLOATS];
+
 // ------------------------------------------------------------------------------------------------
 // Small utilities
 
@@ -326,7 +336,7 @@ __device__ __forceinline__ float total_eps(float eps0, float m, float lab_err, f
 }
 
 // Small tables (KT = 8 or 16, compile time): all KT scores of a pixel stay in registers.
-template <int P, int KT, bool CONV>
+template <int P, int KT, bool CONV, bool CT = false>
 __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, const Pix<P>& px, float lmax,
                                              float cmax, float conv_k, float (&eps)[P], unsigned int (&idx)[P],
                                              bool (&certified)[P]) {
@@ -348,7 +358,14 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
 #pragma unroll
   for (int c = 0; c < KT; c += 8) {
     float f[48];
-    load_chunk(rec_at(tab, c), f);
+    if (CT) {
+      // tab points into the constant bank (dense records): uniform-register operands
+      const float* ct = reinterpret_cast<const float*>(tab) + 6 * c;
+#pragma unroll
+      for (int u = 0; u < 48; ++u) f[u] = ct[u];
+    } else {
+      load_chunk(rec_at(tab, c), f);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -474,6 +491,7 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
+template <bool DENSE = false>
 __device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict__ tab, unsigned int k, bool need,
                                                        float L, float a, float b, float C, float slack,
                                                        unsigned int idx_in) {
@@ -488,13 +506,13 @@ __device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict
     const float pslack = __shfl_sync(0xffffffffu, slack, src);
     const fast::PixCoef pc = fast::pix_coef(pL, pa, pb, pC);
     float m = 3.0e38f;
-    for (unsigned int j = lane; j < k; j += 32) m = fminf(m, score1(pc, rec_at(tab, j)->q));
+    for (unsigned int j = lane; j < k; j += 32) m = fminf(m, score1(pc, (DENSE ? tab + j : rec_at(tab, j))->q));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
     const float bound = m + pslack;
     unsigned long long best = ~0ull;
     for (unsigned int j = lane; j < k; j += 32) {
-      const CentRec r = *rec_at(tab, j);
+      const CentRec r = DENSE ? tab[j] : *rec_at(tab, j);
       if (score1(pc, r.q) <= bound) {
         const float d = ex::cie94_c(pL, pa, pb, pC, -r.q[1], -r.q[4], -r.q[5], r.q[3]);
         const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | j;
@@ -814,8 +832,11 @@ __device__ __forceinline__ void lloyd_load(const float4* __restrict__ work, unsi
 
 // One tile of THREADS x P pixels.  KT > 0: compile-time table length (saved-score search);
 // KT == 0: runtime length kp (chunked search).  PRIVATE: thread-private int4 slots in s_acc.
-template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK>
-__device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, unsigned int kp, int4* __restrict__ s_acc,
+// CT: s_tab is the job's slot in the constant bank (argmin) and x_tab the dense table in global
+// memory for the rare exact path; otherwise both are the shared-memory copy.
+template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK, bool CT = false>
+__device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, const CentRec* __restrict__ x_tab,
+                                           unsigned int kp, int4* __restrict__ s_acc,
                                            unsigned long long* __restrict__ g_acc, const float4 (&v)[P],
                                            unsigned long long base, unsigned long long n, unsigned int k,
                                            float lmax, float cmax, unsigned int tid, unsigned int& slow) {
@@ -833,7 +854,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
   unsigned int idx[P];
   bool certified[P];
   if (KT > 0)
-    argmin_small<P, (KT > 0 ? KT : 8), false>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
+    argmin_small<P, (KT > 0 ? KT : 8), false, CT>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
   else
     argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
   // one vote per tile: the exact path is rare (1e-4 .. 1e-2 of the pixels)
@@ -847,7 +868,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (__any_sync(0xffffffffu, need[i])) {
-        idx[i] = warp_exact_argmin(s_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
+        idx[i] = warp_exact_argmin<CT>(x_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
         slow += need[i] ? 1u : 0u;
       }
     }
@@ -876,21 +897,25 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, un
 
 // KT > 0: table of KT entries in static shared memory.  KT == 0: table of pad32(k) entries at the
 // start of dynamic shared memory (followed, if PRIVATE, by the accumulator slots for KCAP clusters).
-template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB>
+// CT (KT > 0, PRIVATE): the table is read from slot `cslot` of the constant bank instead.
+template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB, bool CT = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4* __restrict__ work,
                                                          unsigned long long n, int color_space,
-                                                         int distributed_mode, PeerXchg X) {
+                                                         int distributed_mode, PeerXchg X, int cslot) {
+  static_assert(!CT || (KT > 0 && KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(16) unsigned char s_tab_static[KT > 0 ? (KT / 8) * CHUNK_BYTES : 16];
+  __shared__ __align__(16) unsigned char s_tab_static[(KT > 0 && !CT) ? (KT / 8) * CHUNK_BYTES : 16];
   __shared__ bool s_last;
   JobState* st = J.st;
   if (st->done) return;
   const unsigned int tid = threadIdx.x;
   const unsigned int k = st->k;
   const unsigned int kp = KT > 0 ? (unsigned int)KT : pad32(k);
-  CentRec* s_tab = reinterpret_cast<CentRec*>(KT > 0 ? s_tab_static : smem_raw);
+  const CentRec* s_tab = CT ? reinterpret_cast<const CentRec*>(c_tab[cslot])
+                             : reinterpret_cast<const CentRec*>(KT > 0 ? s_tab_static : smem_raw);
+  const CentRec* x_tab = CT ? J.tab : s_tab;
   int4* s_acc = reinterpret_cast<int4*>(smem_raw + (KT > 0 ? 0 : tab_smem_bytes(pad32(KCAP))));  // [KCAP][THREADS]
-  tab_to_smem(s_tab, J.tab, kp, tid, THREADS);
+  if (!CT) tab_to_smem(const_cast<CentRec*>(s_tab), J.tab, kp, tid, THREADS);
   if (PRIVATE) {
 #pragma unroll 4
     for (int c = 0; c < KCAP; ++c) s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
@@ -932,8 +957,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     for (; tile < full_tiles; tile += gridDim.x) {
       const unsigned long long next = tile + gridDim.x;
       if (next < full_tiles) lloyd_load<THREADS, P, false>(work, next * TILE + tid, n, nxt);
-      lloyd_tile<KT, THREADS, P, PRIVATE, false>(s_tab, kp, s_acc, g_acc, cur, tile * TILE + tid, n, k, lmax, cmax, tid,
-                                                 slow);
+      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT>(s_tab, x_tab, kp, s_acc, g_acc, cur, tile * TILE + tid, n, k, lmax,
+                                                     cmax, tid, slow);
       since_flush += P;
       // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
       if (PRIVATE && since_flush + P > 240) flush();
@@ -946,8 +971,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     if (PRIVATE && since_flush + P > 240) flush();
     float4 tail[P];
     lloyd_load<THREADS, P, true>(work, full_tiles * TILE + tid, n, tail);
-    lloyd_tile<KT, THREADS, P, PRIVATE, true>(s_tab, kp, s_acc, g_acc, tail, full_tiles * TILE + tid, n, k, lmax, cmax,
-                                              tid, slow);
+    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT>(s_tab, x_tab, kp, s_acc, g_acc, tail, full_tiles * TILE + tid, n, k, lmax,
+                                                  cmax, tid, slow);
   }
   flush();
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
