@@ -131,6 +131,14 @@ void kmg_fixed_centroids(const uint8_t* colors_rgba8, uint32_t count, int color_
 void kmg_centroids_to_rgba8(const float* centroids, uint32_t count, int color_space, uint8_t* colors_out);
 /* Sort key of kmeans_palette (core/src/lib.rs:276-284): stable sort of RGBA8 colours by Lab L. */
 void kmg_sort_palette_by_lightness(uint8_t* colors_rgba8, uint32_t count);
+/* operations::extract_palette_octree (core/src/operations.rs:90-97) over ColorTree::{add_color,reduce}
+ * (core/src/octree.rs:41-110): the reference's CPU octree quantiser, CPU here too.  rgba = the
+ * pixels octree_palette hands it (the image, or its <= 128 px shrink from kmg_resize,
+ * core/src/lib.rs:288-316).  colors_out must hold color_count x 4 bytes; *count_out <= color_count
+ * colours are written, sorted as (r,g,b,a) tuples and de-duplicated; the caller then sorts them
+ * with kmg_sort_palette_by_lightness (lib.rs:318-329). */
+int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32_t color_count, uint8_t* colors_out,
+                       uint32_t* count_out);
 
 /* ---- device-resident entry points (inputs already in HBM; used by batch callers, the bench and
  *      the stage-level parity tests).  Pointers are device pointers on ctx's device; `stream` is a

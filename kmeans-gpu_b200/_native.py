@@ -65,6 +65,7 @@ SIGNATURES = {
     "kmg_fixed_centroids": (None, [_u8p, C.c_uint32, C.c_int, _f32p]),
     "kmg_centroids_to_rgba8": (None, [_f32p, C.c_uint32, C.c_int, _u8p]),
     "kmg_sort_palette_by_lightness": (None, [_u8p, C.c_uint32]),
+    "kmg_octree_palette": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, _u8p, _u32p]),
     "kmg_dev_convert": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp]),
     "kmg_dev_resize": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp]),
     "kmg_dev_assign": (C.c_int, [_vp, _vp, C.c_uint64, _f32p, C.c_uint32, _vp, _vp]),

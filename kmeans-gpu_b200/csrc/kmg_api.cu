@@ -31,12 +31,45 @@ using namespace kmg;
 
 // Lloyd-pass variants: <table length (0 = runtime), accumulator capacity, threads, pixels/thread,
 // thread-private accumulators, min blocks/SM>
-#define LLOYD8 k_lloyd<8, 8, 256, 4, true, 2>
-#define LLOYD8C k_lloyd<8, 8, 256, 4, true, 2, true>
-#define LLOYD16 k_lloyd<16, 16, 256, 2, true, 2>
-#define LLOYD32 k_lloyd<0, 32, 128, 4, true, 3>
-#define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
+// Geometry variants of the k <= 8 pass (KMG_LLOYD8_VARIANT selects one; tools/sweep_lloyd8.py times them)
+// Variants of the thread-private Lloyd pass (k <= 32).  The first entry of a class is its default;
+// KMG_LLOYD8_VARIANT / KMG_LLOYD16_VARIANT / KMG_LLOYD32_VARIANT pick another one
+// (tools/sweep_lloyd.py times them all and checks that they produce identical sums).
+typedef void (*lloyd_fn)(JobPtrs, const float4*, unsigned long long, int, int, PeerXchg, int);
+struct LloydVariant {
+  lloyd_fn fn;
+  int kcap, threads, px, const_tab;
+  size_t smem;
+  const char* name;
+};
 static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
+#define LV8(P, MINB, CT, ATOM, T) k_lloyd<8, 8, T, P, true, MINB, CT, ATOM>, 8, T, P, CT, (size_t)8 * T * 16
+#define LV16(P, MINB, CT, ATOM) k_lloyd<16, 16, 256, P, true, MINB, CT, ATOM>, 16, 256, P, CT, (size_t)16 * 256 * 16
+static const LloydVariant LLOYD_VARIANTS[] = {
+    // k <= 8
+    {LV8(4, 2, true, true, 256), "const table, atomic slots, 256 thr x 4 px, 2 blocks/SM"},
+    {LV8(4, 2, false, true, 256), "smem table, atomic slots, 256 thr x 4 px, 2 blocks/SM"},
+    {LV8(4, 2, false, false, 256), "smem table, 128-bit RMW slots, 256 thr x 4 px, 2 blocks/SM"},
+    {LV8(4, 3, true, true, 256), "const table, atomic slots, 256 thr x 4 px, 3 blocks/SM"},
+    {LV8(4, 2, true, false, 256), "const table, RMW slots, 256 thr x 4 px, 2 blocks/SM"},
+    {LV8(2, 3, false, false, 256), "smem table, RMW slots, 256 thr x 2 px, 3 blocks/SM"},
+    // k <= 16
+    {LV16(2, 2, false, false), "smem table, RMW slots, 256 thr x 2 px, 2 blocks/SM"},
+    {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
+    {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
+    {LV16(2, 2, true, false), "const table, RMW slots, 256 thr x 2 px, 2 blocks/SM"},
+    // k <= 32 (chunked search, table in dynamic shared memory)
+    {k_lloyd<0, 32, 128, 4, true, 3, false, false>, 32, 128, 4, 0, LLOYD32_SMEM, "RMW slots, 128 thr x 4 px, 3 blocks/SM"},
+    {k_lloyd<0, 32, 128, 4, true, 3, false, true>, 32, 128, 4, 0, LLOYD32_SMEM, "atomic slots, 128 thr x 4 px, 3 blocks/SM"},
+};
+static constexpr int N_LLOYD_VARIANTS = (int)(sizeof(LLOYD_VARIANTS) / sizeof(LLOYD_VARIANTS[0]));
+// index in LLOYD_VARIANTS of variant v of class kcap (-1: none)
+static int lloyd_variant_index(int kcap, int v) {
+  for (int i = 0; i < N_LLOYD_VARIANTS; ++i)
+    if (LLOYD_VARIANTS[i].kcap == kcap && v-- == 0) return i;
+  return -1;
+}
+#define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
 // Whole-k-means-in-one-launch variants (kmg_small.cuh): <table/accumulator capacity, threads>
 #define SMALL8 k_kmeans_small<8, 512>
 #define SMALL16 k_kmeans_small<16, 512>
@@ -166,7 +199,9 @@ struct kmg_ctx {
   std::mutex mu;
   std::vector<Workspace*> pool;
   std::atomic<uint64_t> launches{0};
-  int occ_private8 = 1, occ_private16 = 1, occ_private32 = 1;
+  int lloyd_sel[3] = {0, 0, 0};    // LLOYD_VARIANTS index in use for k <= 8 / 16 / 32
+  int lloyd_nocst[3] = {0, 0, 0};  // ... and the one taken when no constant-bank slot is free
+  int occ_lloyd[32] = {0};
   // fused small-image k-means: dynamic shared memory available per variant (0 = not launchable)
   // and whether clusters of 8 / 16 CTAs can be scheduled
   size_t small_dyn[3] = {0, 0, 0};
@@ -183,8 +218,7 @@ struct kmg_ctx {
   void* mbox_peer[MAX_PEERS] = {nullptr};  // every rank's mailbox as mapped here (own entry = mbox_own)
   uint32_t xchg_seq = 0x1234567u;          // flag sequence base handed to the next sharded job
   // constant-bank table slots (kmg_kernels.cuh: c_tab), handed to jobs with k <= 8
-  void* c_tab_dev = nullptr;  // nullptr: constant-bank tables switched off (KMG_NO_CONST_TABLE)
-  int occ_const8 = 1;
+  void* c_tab_dev = nullptr;
 };
 
 struct kmg_job {
@@ -504,21 +538,33 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   CHECK_LAUNCH();
   // opt in to > 48 KiB dynamic shared memory
   const int big = (int)(tab_smem_bytes(MAX_K) + MAX_K * 4);
-  CU(cudaFuncSetAttribute(LLOYD8, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD16, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LLOYD32_SMEM));
   CU(cudaFuncSetAttribute(LLOYDG, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_assign<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<0, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap<1, 0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
   small_probe(ctx, prop);
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private8, LLOYD8, 256, 8 * 256 * 16));
-  CU(cudaFuncSetAttribute(LLOYD8C, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_const8, LLOYD8C, 256, 8 * 256 * 16));
-  if (!getenv("KMG_NO_CONST_TABLE")) CU(cudaGetSymbolAddress(&ctx->c_tab_dev, c_tab));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private16, LLOYD16, 256, 16 * 256 * 16));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_private32, LLOYD32, 128, LLOYD32_SMEM));
+  CU(cudaGetSymbolAddress(&ctx->c_tab_dev, c_tab));
+  for (int v = 0; v < N_LLOYD_VARIANTS; ++v) {
+    const LloydVariant& V = LLOYD_VARIANTS[v];
+    CU(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_lloyd[v], V.fn, V.threads, V.smem));
+  }
+  {
+    static const int kcaps[3] = {8, 16, 32};
+    static const char* envs[3] = {"KMG_LLOYD8_VARIANT", "KMG_LLOYD16_VARIANT", "KMG_LLOYD32_VARIANT"};
+    for (int c = 0; c < 3; ++c) {
+      int sel = lloyd_variant_index(kcaps[c], 0);
+      if (const char* e = getenv(envs[c])) {
+        int i = lloyd_variant_index(kcaps[c], atoi(e));
+        if (i >= 0) sel = i;
+      }
+      ctx->lloyd_sel[c] = sel;
+      int alt = sel;  // first variant of the class that does not need the constant bank
+      for (int v = 0; LLOYD_VARIANTS[alt].const_tab; ++v) alt = lloyd_variant_index(kcaps[c], v);
+      ctx->lloyd_nocst[c] = alt;
+    }
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   *out = ctx;
   return KMG_OK;
@@ -628,27 +674,22 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   const bool fused = dist && ctx->p2p;
   const int partial = dist ? (fused ? 2 : 1) : 0;
   const PeerXchg X = peer_xchg(ctx, j, fused);
-  if (j->k <= 8) {
-    if (j->cslot < 0 && !j->cslot_tried) {
-      j->cslot_tried = true;
-      j->cslot = cslot_acquire(ctx);
+  if (j->k <= 32) {
+    const int cls = j->k <= 8 ? 0 : j->k <= 16 ? 1 : 2;
+    int v = ctx->lloyd_sel[cls];
+    if (LLOYD_VARIANTS[v].const_tab) {
+      if (j->cslot < 0 && !j->cslot_tried) {
+        j->cslot_tried = true;
+        j->cslot = cslot_acquire(ctx);
+      }
+      if (j->cslot < 0) v = ctx->lloyd_nocst[cls];  // no free slot in the constant bank: shared-memory table
     }
-    if (j->cslot >= 0) {
-      // the table of this pass goes to the job's slot of the constant bank (see c_tab)
-      CU(cudaMemcpyAsync((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4, j->P.tab, 8 * sizeof(CentRec),
-                         cudaMemcpyDeviceToDevice, s));
-      int grid = grid_for(ctx, n, 256 * 4, ctx->occ_const8);
-      LLOYD8C<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X, j->cslot);
-    } else {
-      int grid = grid_for(ctx, n, 256 * 4, ctx->occ_private8);
-      LLOYD8<<<grid, 256, 8 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
-    }
-  } else if (j->k <= 16) {
-    int grid = grid_for(ctx, n, 256 * 2, ctx->occ_private16);
-    LLOYD16<<<grid, 256, 16 * 256 * 16, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
-  } else if (j->k <= 32) {
-    int grid = grid_for(ctx, n, 128 * 4, ctx->occ_private32);
-    LLOYD32<<<grid, 128, LLOYD32_SMEM, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
+    const LloydVariant& V = LLOYD_VARIANTS[v];
+    if (V.const_tab)  // the table of this pass goes to the job's slot of the constant bank (see c_tab)
+      CU(cudaMemcpyAsync((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4, j->P.tab,
+                         (size_t)V.kcap * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
+    int grid = grid_for(ctx, n, V.threads * V.px, ctx->occ_lloyd[v]);
+    V.fn<<<grid, V.threads, V.smem, s>>>(j->P, j->work, n, j->color_space, partial, X, V.const_tab ? j->cslot : 0);
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k));
     int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);

@@ -111,3 +111,117 @@ extern "C" void kmg_sort_palette_by_lightness(uint8_t* colors, uint32_t count) {
   std::vector<uint8_t> tmp(colors, colors + (size_t)count * 4);
   for (uint32_t i = 0; i < count; ++i) std::memcpy(colors + 4 * i, tmp.data() + 4 * order[i], 4);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Octree quantiser — `Algorithm::Octree` of the reference.  It is CPU code there as well
+// (core/src/octree.rs, driven by operations::extract_palette_octree, core/src/operations.rs:90-97,
+// on the <= 128 px shrink that octree_palette makes, core/src/lib.rs:288-331); a Rust caller keeps
+// octree.rs as it is, this entry point gives non-Rust callers the same palette.
+//
+// Restated behaviour: an 8-level tree keyed by the r/g/b bits from the most significant one down
+// (octree.rs:12-26); a node created while walking level L carries `level = L`, so leaves have
+// level 7 (octree.rs:45-57); every pixel is added to its leaf.  reduce(): all nodes that hold
+// pixels, ordered by (child_count, pixel_count >> level, node id) — octree.rs:246-266 — are merged
+// smallest first into their parents until at most `color_count` remain (octree.rs:66-110); a popped
+// node without a parent (the root) is dropped.  The palette is the integer mean of every remaining
+// node, sorted as (r,g,b,a) tuples and de-duplicated (octree.rs:104-109,128-135).
+namespace {
+
+struct OctNode {
+  uint32_t level = 0;
+  uint32_t color_index = 0;
+  int64_t parent = -1;
+  int64_t children[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  uint32_t child_count = 0;
+  uint64_t count = 0, r = 0, g = 0, b = 0;
+};
+
+struct OctLess {  // Node::partial_cmp, octree.rs:246-266 (a strict total order: ids are distinct)
+  const std::vector<OctNode>* nodes;
+  bool operator()(size_t a, size_t b) const {
+    if (a == b) return false;
+    const OctNode& x = (*nodes)[a];
+    const OctNode& y = (*nodes)[b];
+    if (x.child_count != y.child_count) return x.child_count < y.child_count;
+    const uint64_t xc = x.count >> x.level, yc = y.count >> y.level;
+    if (xc != yc) return xc < yc;
+    return a < b;
+  }
+};
+
+}  // namespace
+
+extern "C" int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32_t color_count, uint8_t* colors_out,
+                                  uint32_t* count_out) {
+  if (!count_out || (n_pixels && !rgba) || (color_count && !colors_out)) return KMG_ERR_BAD_ARG;
+  *count_out = 0;
+  if (color_count == 0) return KMG_OK;  // octree.rs:67-69
+  std::vector<OctNode> nodes(1);
+  for (uint64_t p = 0; p < n_pixels; ++p) {
+    const uint8_t* c = rgba + 4 * p;
+    size_t at = 0;
+    for (uint32_t level = 0; level < 8; ++level) {
+      const uint8_t mask = (uint8_t)(0x80u >> level);
+      const uint32_t ci = ((c[0] & mask) ? 4u : 0u) | ((c[1] & mask) ? 2u : 0u) | ((c[2] & mask) ? 1u : 0u);
+      if (nodes[at].children[ci] < 0) {
+        OctNode child;
+        child.level = level;
+        child.color_index = ci;
+        child.parent = (int64_t)at;
+        nodes[at].children[ci] = (int64_t)nodes.size();
+        nodes[at].child_count += 1;
+        nodes.push_back(child);
+      }
+      at = (size_t)nodes[at].children[ci];
+    }
+    nodes[at].r += c[0];
+    nodes[at].g += c[1];
+    nodes[at].b += c[2];
+    nodes[at].count += 1;
+  }
+  // Like the reference: a sequence kept in descending order whose back (the smallest node) is
+  // popped.  Node keys only change while the node is outside the sequence, so it is always sorted
+  // and the binary searches are exact.
+  OctLess less{&nodes};
+  auto greater = [&](size_t a, size_t b) { return less(b, a); };
+  std::vector<size_t> leaves;
+  for (size_t i = 0; i < nodes.size(); ++i)
+    if (nodes[i].count > 0) leaves.push_back(i);
+  std::sort(leaves.begin(), leaves.end(), greater);
+  while (leaves.size() > color_count) {
+    const size_t id = leaves.back();
+    leaves.pop_back();
+    OctNode& node = nodes[id];
+    if (node.parent < 0) continue;
+    const size_t pid = (size_t)node.parent;
+    auto it = std::lower_bound(leaves.begin(), leaves.end(), pid, greater);
+    if (it != leaves.end() && *it == pid) leaves.erase(it);
+    OctNode& par = nodes[pid];
+    par.r += node.r;
+    par.g += node.g;
+    par.b += node.b;
+    par.count += node.count;
+    par.child_count -= 1;
+    par.children[node.color_index] = -1;
+    node.parent = -1;
+    it = std::lower_bound(leaves.begin(), leaves.end(), pid, greater);
+    if (it == leaves.end() || *it != pid) leaves.insert(it, pid);
+  }
+  std::vector<uint32_t> pal;
+  for (size_t id : leaves) {
+    const OctNode& n = nodes[id];
+    const uint32_t r = (uint32_t)(n.r / n.count) & 255u, g = (uint32_t)(n.g / n.count) & 255u,
+                   b = (uint32_t)(n.b / n.count) & 255u;
+    pal.push_back((r << 24) | (g << 16) | (b << 8) | 255u);  // big-endian tuple order for the sort
+  }
+  std::sort(pal.begin(), pal.end());
+  pal.erase(std::unique(pal.begin(), pal.end()), pal.end());
+  for (size_t i = 0; i < pal.size(); ++i) {
+    colors_out[4 * i + 0] = (uint8_t)(pal[i] >> 24);
+    colors_out[4 * i + 1] = (uint8_t)(pal[i] >> 16);
+    colors_out[4 * i + 2] = (uint8_t)(pal[i] >> 8);
+    colors_out[4 * i + 3] = 255;
+  }
+  *count_out = (uint32_t)pal.size();
+  return KMG_OK;
+}

@@ -125,6 +125,13 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
   }
   return v;
 }
+// Sum of one int32 per lane (any values) with two REDUX: the signed high 16 bits and the unsigned
+// low 16 bits are reduced separately, neither partial sum can overflow 32 bits.
+__device__ __forceinline__ long long warp_sum_i32(int v) {
+  const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+  const unsigned int lo = __reduce_add_sync(0xffffffffu, (unsigned int)v & 0xffffu);
+  return (long long)hi * 65536 + (long long)lo;
+}
 __device__ __forceinline__ long long warp_sum_i64(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -834,9 +841,13 @@ __device__ __forceinline__ void lloyd_load(const float4* __restrict__ work, unsi
 // KT == 0: runtime length kp (chunked search).  PRIVATE: thread-private int4 slots in s_acc.
 // CT: s_tab is the job's slot in the constant bank (argmin) and x_tab the dense table in global
 // memory for the rare exact path; otherwise both are the shared-memory copy.
-template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK, bool CT = false>
+// ATOM (with PRIVATE): the private slots are laid out [component][cluster][thread] and updated with
+// four fire-and-forget shared-memory atomic adds per pixel instead of a 128-bit read-modify-write,
+// whose load -> add -> store chains serialise when two pixels of a thread share a cluster (the
+// compiler has to assume they do); cstride = distance between components in ints.
+template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK, bool CT = false, bool ATOM = false>
 __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, const CentRec* __restrict__ x_tab,
-                                           unsigned int kp, int4* __restrict__ s_acc,
+                                           unsigned int kp, int4* __restrict__ s_acc, unsigned int cstride,
                                            unsigned long long* __restrict__ g_acc, const float4 (&v)[P],
                                            unsigned long long base, unsigned long long n, unsigned int k,
                                            float lmax, float cmax, unsigned int tid, unsigned int& slow) {
@@ -876,7 +887,13 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     if (valid[i]) {
-      if (PRIVATE) {
+      if (PRIVATE && ATOM) {
+        int* slot = reinterpret_cast<int*>(s_acc) + idx[i] * THREADS + tid;
+        atomicAdd(slot, ex::to_fixed(px.L[i]));
+        atomicAdd(slot + cstride, ex::to_fixed(px.a[i]));
+        atomicAdd(slot + 2 * cstride, ex::to_fixed(px.b[i]));
+        atomicAdd(slot + 3 * cstride, 1);
+      } else if (PRIVATE) {
         int4* slot = s_acc + idx[i] * THREADS + tid;
         int4 a = *slot;
         a.x += ex::to_fixed(px.L[i]);
@@ -898,7 +915,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
 // KT > 0: table of KT entries in static shared memory.  KT == 0: table of pad32(k) entries at the
 // start of dynamic shared memory (followed, if PRIVATE, by the accumulator slots for KCAP clusters).
 // CT (KT > 0, PRIVATE): the table is read from slot `cslot` of the constant bank instead.
-template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB, bool CT = false>
+template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB, bool CT = false, bool ATOM = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4* __restrict__ work,
                                                          unsigned long long n, int color_space,
                                                          int distributed_mode, PeerXchg X, int cslot) {
@@ -916,6 +933,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
   const CentRec* x_tab = CT ? J.tab : s_tab;
   int4* s_acc = reinterpret_cast<int4*>(smem_raw + (KT > 0 ? 0 : tab_smem_bytes(pad32(KCAP))));  // [KCAP][THREADS]
   if (!CT) tab_to_smem(const_cast<CentRec*>(s_tab), J.tab, kp, tid, THREADS);
+  constexpr unsigned int CSTRIDE = (unsigned int)(KCAP > 0 ? KCAP : 1) * THREADS;
   if (PRIVATE) {
 #pragma unroll 4
     for (int c = 0; c < KCAP; ++c) s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
@@ -935,10 +953,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     // needed: a warp only reads what it wrote) and sends 4 reductions per cluster to L2.
     const unsigned int lane = tid & 31;
     for (unsigned int c = 0; c < k; ++c) {
-      int4 v = s_acc[c * THREADS + tid];
-      s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
-      long long s0 = warp_sum_i64(v.x), s1 = warp_sum_i64(v.y), s2 = warp_sum_i64(v.z), s3 = warp_sum_i64(v.w);
-      if (lane == 0 && s3 != 0) {
+      int4 v;
+      if (ATOM) {
+        int* slot = reinterpret_cast<int*>(s_acc) + c * THREADS + tid;
+        v = make_int4(slot[0], slot[CSTRIDE], slot[2 * CSTRIDE], slot[3 * CSTRIDE]);
+        slot[0] = 0;
+        slot[CSTRIDE] = 0;
+        slot[2 * CSTRIDE] = 0;
+        slot[3 * CSTRIDE] = 0;
+      } else {
+        v = s_acc[c * THREADS + tid];
+        s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
+      }
+      const long long s3 = (long long)__reduce_add_sync(0xffffffffu, v.w);  // <= 32 x 240
+      if (s3 == 0) continue;                                                  // warp-uniform
+      const long long s0 = warp_sum_i32(v.x), s1 = warp_sum_i32(v.y), s2 = warp_sum_i32(v.z);
+      if (lane == 0) {
         atomicAdd(g_acc + c * 4 + 0, (unsigned long long)s0);
         atomicAdd(g_acc + c * 4 + 1, (unsigned long long)s1);
         atomicAdd(g_acc + c * 4 + 2, (unsigned long long)s2);
@@ -957,8 +987,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     for (; tile < full_tiles; tile += gridDim.x) {
       const unsigned long long next = tile + gridDim.x;
       if (next < full_tiles) lloyd_load<THREADS, P, false>(work, next * TILE + tid, n, nxt);
-      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT>(s_tab, x_tab, kp, s_acc, g_acc, cur, tile * TILE + tid, n, k, lmax,
-                                                     cmax, tid, slow);
+      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, cur, tile * TILE + tid, n,
+                                                           k, lmax, cmax, tid, slow);
       since_flush += P;
       // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
       if (PRIVATE && since_flush + P > 240) flush();
@@ -971,8 +1001,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     if (PRIVATE && since_flush + P > 240) flush();
     float4 tail[P];
     lloyd_load<THREADS, P, true>(work, full_tiles * TILE + tid, n, tail);
-    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT>(s_tab, x_tab, kp, s_acc, g_acc, tail, full_tiles * TILE + tid, n, k, lmax,
-                                                  cmax, tid, slow);
+    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, tail,
+                                                        full_tiles * TILE + tid, n, k, lmax, cmax, tid, slow);
   }
   flush();
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);

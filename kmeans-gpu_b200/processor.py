@@ -144,6 +144,19 @@ def sort_palette_by_lightness(colors_rgba8) -> np.ndarray:
     return cols
 
 
+def octree_colors(pixels_rgba8, color_count: int) -> np.ndarray:
+    """operations::extract_palette_octree (core/src/operations.rs:90-97): the reference's CPU octree
+    quantiser over the given pixels; <= color_count colours sorted as (r,g,b,a) tuples."""
+    px = np.ascontiguousarray(pixels_rgba8, dtype=np.uint8).reshape(-1, 4)
+    out = np.empty((max(int(color_count), 1), 4), np.uint8)
+    n = C.c_uint32(0)
+    code = _native.load().kmg_octree_palette(px.ctypes.data_as(C.POINTER(C.c_uint8)), px.shape[0], int(color_count),
+                                             out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n))
+    if code != 0:
+        raise KmgError(code, "kmg_octree_palette: bad argument")
+    return out[: n.value].copy()
+
+
 def resized_dims(w: int, h: int, max_size: int = 256):
     ow, oh = C.c_uint32(), C.c_uint32()
     _native.load().kmg_resized_dims(w, h, max_size, C.byref(ow), C.byref(oh))
@@ -219,11 +232,19 @@ class ImageProcessor:
     def palette(self, color_count: int, image, algo: Algorithm = Algorithm.Kmeans, opts: Opts | None = None,
                 color_space: ColorSpace = ColorSpace.Lab) -> np.ndarray:
         """lib.rs:67-77 + kmeans_palette :255-286: k colours (RGBA8, alpha 255) sorted by Lab L."""
-        if algo is not Algorithm.Kmeans:
-            raise KmgError(5, "Algorithm::Octree is the reference's CPU quantiser (core/src/octree.rs); "
-                              "it is outside the CUDA hot path")
+        if algo is Algorithm.Octree:
+            return self.octree_palette(color_count, image)
         cent, _ = self.kmeans_centroids(color_count, image, color_space, opts)
         return sort_palette_by_lightness(centroids_to_rgba8(cent, color_space))
+
+    def octree_palette(self, color_count: int, image) -> np.ndarray:
+        """octree_palette (core/src/lib.rs:288-331): shrink to <= 128 px on the device
+        (InputTexture::resized + pull_image), quantise on the CPU as the reference does
+        (core/src/octree.rs), sort by Lab L."""
+        img = _as_image(image)
+        w, h = img.dimensions
+        pixels = self.resize(img, 128).rgba if (w > 128 or h > 128) else img.rgba
+        return sort_palette_by_lightness(octree_colors(pixels, color_count))
 
     def find(self, image, colors, reduce_mode: ReduceMode = ReduceMode.Replace,
              color_space: ColorSpace = ColorSpace.Lab, out: np.ndarray | None = None) -> Image:
@@ -236,9 +257,13 @@ class ImageProcessor:
                color_space: ColorSpace = ColorSpace.Lab, return_details: bool = False,
                out: np.ndarray | None = None):
         """lib.rs:116-164.  `out`: optional (h, w, 4) uint8 result buffer (e.g. from pinned_empty)."""
-        if algo is not Algorithm.Kmeans:
-            raise KmgError(5, "Algorithm::Octree is the reference's CPU quantiser (core/src/octree.rs); "
-                              "feed its palette to find() instead")
+        if algo is Algorithm.Octree:
+            # lib.rs:133-136: the octree palette goes through fixed_centroids into the same remap
+            colors = self.octree_palette(color_count, image)
+            res = self.find(image, colors, reduce_mode, color_space, out=out)
+            if return_details:
+                return res, fixed_centroids(colors, color_space), 0
+            return res
         img = _as_image(image)
         w, h = img.dimensions
         out = _out_image(out, h, w)

@@ -471,8 +471,6 @@ def test_errors(proc, K, tokyo):
     with pytest.raises(K.KmgError):
         proc.reduce(5000, tokyo)  # above MAX_K
     with pytest.raises(K.KmgError):
-        proc.palette(8, tokyo, K.Algorithm.Octree)
-    with pytest.raises(K.KmgError):
         proc.kmeans_centroids(4, tokyo, opts=K.Opts(seed_x=100000, seed_y=0))
     # the context is still usable afterwards
     assert proc.find(tokyo[:8, :8], DARK_WHITE_RED).dimensions == (8, 8)
