@@ -35,7 +35,7 @@ using namespace kmg;
 // Variants of the thread-private Lloyd pass (k <= 32).  The first entry of a class is its default;
 // KMG_LLOYD8_VARIANT / KMG_LLOYD16_VARIANT / KMG_LLOYD32_VARIANT pick another one
 // (tools/sweep_lloyd.py times them all and checks that they produce identical sums).
-typedef void (*lloyd_fn)(JobPtrs, const float4*, unsigned long long, int, int, PeerXchg, int);
+typedef void (*lloyd_fn)(JobPtrs, const float4*, unsigned long long, int, int, PeerXchg, int, unsigned int);
 struct LloydVariant {
   lloyd_fn fn;
   int kcap, threads, px, const_tab;
@@ -54,13 +54,13 @@ static const LloydVariant LLOYD_VARIANTS[] = {
     {LV8(4, 2, true, false, 256), "const table, RMW slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(2, 3, false, false, 256), "smem table, RMW slots, 256 thr x 2 px, 3 blocks/SM"},
     // k <= 16
-    {LV16(2, 2, false, false), "smem table, RMW slots, 256 thr x 2 px, 2 blocks/SM"},
-    {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
     {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
+    {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
+    {LV16(2, 2, false, false), "smem table, RMW slots, 256 thr x 2 px, 2 blocks/SM"},
     {LV16(2, 2, true, false), "const table, RMW slots, 256 thr x 2 px, 2 blocks/SM"},
     // k <= 32 (chunked search, table in dynamic shared memory)
-    {k_lloyd<0, 32, 128, 4, true, 3, false, false>, 32, 128, 4, 0, LLOYD32_SMEM, "RMW slots, 128 thr x 4 px, 3 blocks/SM"},
     {k_lloyd<0, 32, 128, 4, true, 3, false, true>, 32, 128, 4, 0, LLOYD32_SMEM, "atomic slots, 128 thr x 4 px, 3 blocks/SM"},
+    {k_lloyd<0, 32, 128, 4, true, 3, false, false>, 32, 128, 4, 0, LLOYD32_SMEM, "RMW slots, 128 thr x 4 px, 3 blocks/SM"},
 };
 static constexpr int N_LLOYD_VARIANTS = (int)(sizeof(LLOYD_VARIANTS) / sizeof(LLOYD_VARIANTS[0]));
 // index in LLOYD_VARIANTS of variant v of class kcap (-1: none)
@@ -70,6 +70,9 @@ static int lloyd_variant_index(int kcap, int v) {
   return -1;
 }
 #define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
+#define LLOYDGC k_lloyd<0, 0, 256, 4, false, 2, true>  // chunk loop fed from the constant bank (k <= CTAB_BIG_K)
+#define LLOYDGS k_lloyd<0, 0, 256, 4, false, 2, false, true>  // block accumulators in shared memory
+static constexpr uint32_t LLOYDGS_MAX_K = 2048;  // table 52 KiB + accumulators 56 KiB per block
 // Whole-k-means-in-one-launch variants (kmg_small.cuh): <table/accumulator capacity, threads>
 #define SMALL8 k_kmeans_small<8, 512>
 #define SMALL16 k_kmeans_small<16, 512>
@@ -219,6 +222,9 @@ struct kmg_ctx {
   uint32_t xchg_seq = 0x1234567u;          // flag sequence base handed to the next sharded job
   // constant-bank table slots (kmg_kernels.cuh: c_tab), handed to jobs with k <= 8
   void* c_tab_dev = nullptr;
+  void* c_tab_big_dev = nullptr;
+  bool big_const = false;      // KMG_LLOYDG_CONST=1: chunk loop of the k > 32 pass fed from the constant bank (slower)
+  bool big_block_acc = true;   // KMG_LLOYDG_BLOCKACC=0: accumulate through L2 atomics instead of shared memory
 };
 
 struct kmg_job {
@@ -248,15 +254,15 @@ struct kmg_job {
 // The constant bank belongs to the device (one copy of the module per device), not to a context:
 // the free list is per device and process-wide.
 static std::mutex g_cslot_mu;
-static std::vector<int> g_cslots_free[64];
-static bool g_cslots_ready[64];
-static int cslot_acquire(kmg_ctx* ctx) {
+static std::vector<int> g_cslots_free[2][64];  // [small | big tables][device]
+static bool g_cslots_ready[2][64];
+static int cslot_acquire(kmg_ctx* ctx, bool big = false) {
   if (!ctx->c_tab_dev || ctx->device >= 64) return -1;
   std::lock_guard<std::mutex> g(g_cslot_mu);
-  std::vector<int>& fl = g_cslots_free[ctx->device];
-  if (!g_cslots_ready[ctx->device]) {
-    g_cslots_ready[ctx->device] = true;
-    for (int i = CTAB_SLOTS - 1; i >= 0; --i) fl.push_back(i);
+  std::vector<int>& fl = g_cslots_free[big][ctx->device];
+  if (!g_cslots_ready[big][ctx->device]) {
+    g_cslots_ready[big][ctx->device] = true;
+    for (int i = (big ? CTAB_BIG_SLOTS : CTAB_SLOTS) - 1; i >= 0; --i) fl.push_back(i);
   }
   if (fl.empty()) return -1;
   int s = fl.back();
@@ -268,7 +274,7 @@ static int cslot_acquire(kmg_ctx* ctx) {
 kmg_job::~kmg_job() {
   if (cslot >= 0 && ctx) {
     std::lock_guard<std::mutex> g(g_cslot_mu);
-    g_cslots_free[ctx->device].push_back(cslot);
+    g_cslots_free[k > 32 ? 1 : 0][ctx->device].push_back(cslot);
   }
 }
 
@@ -545,6 +551,11 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
   small_probe(ctx, prop);
   CU(cudaGetSymbolAddress(&ctx->c_tab_dev, c_tab));
+  CU(cudaGetSymbolAddress(&ctx->c_tab_big_dev, c_tab_big));
+  if (const char* e = getenv("KMG_LLOYDG_CONST")) ctx->big_const = atoi(e) != 0;
+  if (const char* e = getenv("KMG_LLOYDG_BLOCKACC")) ctx->big_block_acc = atoi(e) != 0;
+  CU(cudaFuncSetAttribute(LLOYDGS, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU(cudaFuncSetAttribute(LLOYDGC, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   for (int v = 0; v < N_LLOYD_VARIANTS; ++v) {
     const LloydVariant& V = LLOYD_VARIANTS[v];
     CU(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.smem));
@@ -689,11 +700,25 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
       CU(cudaMemcpyAsync((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4, j->P.tab,
                          (size_t)V.kcap * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
     int grid = grid_for(ctx, n, V.threads * V.px, ctx->occ_lloyd[v]);
-    V.fn<<<grid, V.threads, V.smem, s>>>(j->P, j->work, n, j->color_space, partial, X, V.const_tab ? j->cslot : 0);
+    V.fn<<<grid, V.threads, V.smem, s>>>(j->P, j->work, n, j->color_space, partial, X, V.const_tab ? j->cslot : 0, j->k);
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k));
     int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
-    LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0);
+    if (j->k <= (uint32_t)CTAB_BIG_K && ctx->big_const && !ctx->big_block_acc && j->cslot < 0 && !j->cslot_tried) {
+      j->cslot_tried = true;
+      j->cslot = cslot_acquire(ctx, true);
+    }
+    if (j->k <= LLOYDGS_MAX_K && ctx->big_block_acc) {
+      smem += (size_t)7 * pad32(j->k) * 4;
+      grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
+      LLOYDGS<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0, j->k);
+    } else if (j->cslot >= 0) {
+      CU(cudaMemcpyAsync((char*)ctx->c_tab_big_dev + (size_t)j->cslot * CTAB_BIG_K * 24, j->P.tab,
+                         (size_t)pad32(j->k) * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
+      LLOYDGC<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, j->cslot, j->k);
+    } else {
+      LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0, j->k);
+    }
   }
   LAUNCHED(ctx);
   CHECK_LAUNCH();

@@ -111,6 +111,12 @@ __device__ __forceinline__ void tab_to_smem(CentRec* s_tab, const CentRec* __res
 constexpr int CTAB_SLOTS = 64;
 constexpr int CTAB_FLOATS = 16 * 6;
 __constant__ float c_tab[CTAB_SLOTS][CTAB_FLOATS];
+// ... and of a table of up to 256 centroids (chunked search): the main loop over chunks reads its
+// 48 scalars per chunk with twelve uniform 128-bit constant loads instead of twelve LDS.128 into
+// vector registers, and its FFMA2 no longer pay the third register-bank read of a vector scalar.
+constexpr int CTAB_BIG_SLOTS = 6;
+constexpr int CTAB_BIG_K = 256;
+__constant__ float c_tab_big[CTAB_BIG_SLOTS][CTAB_BIG_K * 6];
 
 // ------------------------------------------------------------------------------------------------
 // Small utilities
@@ -406,10 +412,11 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
 // and second-best chunk minima.  The precise certificate then runs on the winning chunk alone, so
 // the half-rate ALU pipe sees ~1.1 min/select operations per (pixel, centroid) instead of 5 and
 // the loop is bound by the 5 FMAs of the score.
-template <int P, bool CONV>
+template <int P, bool CONV, bool CT = false>
 __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
                                                float lmax, float cmax, float conv_k, float (&eps)[P],
-                                               unsigned int (&idx)[P], bool (&certified)[P]) {
+                                               unsigned int (&idx)[P], bool (&certified)[P],
+                                               const float* __restrict__ ctab = nullptr) {
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::PixCoef pc[P];
@@ -426,10 +433,18 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
     m2c[i] = 3.0e38f;
     ic[i] = 0;
   }
+  const float* ct = ctab;  // CT: the same table, dense, in the constant bank (uniform-register operands)
+#pragma unroll 1
   for (unsigned int c = 0; c < kp; c += 8) {
     fast::f32x2 s2[8][H];
     float f[48];
-    load_chunk(rec_at(tab, c), f);
+    if (CT) {
+#pragma unroll
+      for (int u = 0; u < 48; ++u) f[u] = ct[u];
+      ct += 48;
+    } else {
+      load_chunk(rec_at(tab, c), f);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -847,7 +862,8 @@ __device__ __forceinline__ void lloyd_load(const float4* __restrict__ work, unsi
 // compiler has to assume they do); cstride = distance between components in ints.
 template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK, bool CT = false, bool ATOM = false>
 __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, const CentRec* __restrict__ x_tab,
-                                           unsigned int kp, int4* __restrict__ s_acc, unsigned int cstride,
+                                           const float* __restrict__ ctab_big, unsigned int kp,
+                                           int4* __restrict__ s_acc, unsigned int cstride,
                                            unsigned long long* __restrict__ g_acc, const float4 (&v)[P],
                                            unsigned long long base, unsigned long long n, unsigned int k,
                                            float lmax, float cmax, unsigned int tid, unsigned int& slow) {
@@ -867,7 +883,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
   if (KT > 0)
     argmin_small<P, (KT > 0 ? KT : 8), false, CT>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
   else
-    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
+    argmin_chunked<P, false, CT>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified, ctab_big);
   // one vote per tile: the exact path is rare (1e-4 .. 1e-2 of the pixels)
   bool need[P], any_need = false;
 #pragma unroll
@@ -879,7 +895,8 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (__any_sync(0xffffffffu, need[i])) {
-        idx[i] = warp_exact_argmin<CT>(x_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], eps[i], idx[i]);
+        idx[i] = warp_exact_argmin<(CT && KT > 0)>(x_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], eps[i],
+                                                   idx[i]);
         slow += need[i] ? 1u : 0u;
       }
     }
@@ -887,7 +904,20 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     if (valid[i]) {
-      if (PRIVATE && ATOM) {
+      if (!PRIVATE && ATOM) {
+        // block accumulators [7][kp]: every fixed-point value goes in as its low 12 bits (unsigned)
+        // and its high part (signed), so 32-bit sums cannot overflow for 2^19 pixels per block and
+        // seven fire-and-forget shared-memory atomics replace four 64-bit reductions through L2
+        int* a = reinterpret_cast<int*>(s_acc) + idx[i];
+        const int f0 = ex::to_fixed(px.L[i]), f1 = ex::to_fixed(px.a[i]), f2 = ex::to_fixed(px.b[i]);
+        atomicAdd(a, f0 & 0xfff);
+        atomicAdd(a + cstride, f0 >> 12);
+        atomicAdd(a + 2 * cstride, f1 & 0xfff);
+        atomicAdd(a + 3 * cstride, f1 >> 12);
+        atomicAdd(a + 4 * cstride, f2 & 0xfff);
+        atomicAdd(a + 5 * cstride, f2 >> 12);
+        atomicAdd(a + 6 * cstride, 1);
+      } else if (PRIVATE && ATOM) {
         int* slot = reinterpret_cast<int*>(s_acc) + idx[i] * THREADS + tid;
         atomicAdd(slot, ex::to_fixed(px.L[i]));
         atomicAdd(slot + cstride, ex::to_fixed(px.a[i]));
@@ -918,26 +948,37 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
 template <int KT, int KCAP, int THREADS, int P, bool PRIVATE, int MINB, bool CT = false, bool ATOM = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4* __restrict__ work,
                                                          unsigned long long n, int color_space,
-                                                         int distributed_mode, PeerXchg X, int cslot) {
-  static_assert(!CT || (KT > 0 && KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k");
+                                                         int distributed_mode, PeerXchg X, int cslot,
+                                                         unsigned int k_arg) {
+  static_assert(!CT || KT == 0 || (KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(16) unsigned char s_tab_static[(KT > 0 && !CT) ? (KT / 8) * CHUNK_BYTES : 16];
   __shared__ bool s_last;
   JobState* st = J.st;
   if (st->done) return;
   const unsigned int tid = threadIdx.x;
-  const unsigned int k = st->k;
+  const unsigned int k = k_arg;  // == st->k; a kernel parameter is provably warp-uniform (loop counters over
+                                 // the table then live in uniform registers and can index the constant bank)
   const unsigned int kp = KT > 0 ? (unsigned int)KT : pad32(k);
-  const CentRec* s_tab = CT ? reinterpret_cast<const CentRec*>(c_tab[cslot])
-                             : reinterpret_cast<const CentRec*>(KT > 0 ? s_tab_static : smem_raw);
-  const CentRec* x_tab = CT ? J.tab : s_tab;
-  int4* s_acc = reinterpret_cast<int4*>(smem_raw + (KT > 0 ? 0 : tab_smem_bytes(pad32(KCAP))));  // [KCAP][THREADS]
-  if (!CT) tab_to_smem(const_cast<CentRec*>(s_tab), J.tab, kp, tid, THREADS);
-  constexpr unsigned int CSTRIDE = (unsigned int)(KCAP > 0 ? KCAP : 1) * THREADS;
+  // KT > 0 && CT: no shared-memory table at all; KT == 0 && CT: the shared-memory table serves the
+  // winning-chunk rescan and the exact path, the chunk loop reads the constant bank
+  constexpr bool CT_SMALL = CT && KT > 0;
+  const CentRec* s_tab = CT_SMALL ? reinterpret_cast<const CentRec*>(c_tab[cslot])
+                                  : reinterpret_cast<const CentRec*>(KT > 0 ? s_tab_static : smem_raw);
+  const CentRec* x_tab = CT_SMALL ? J.tab : s_tab;
+  const float* ctab_big = (CT && KT == 0) ? c_tab_big[cslot] : nullptr;
+  // PRIVATE: [KCAP][THREADS] slots after the (compile-time sized) table; !PRIVATE && ATOM: block
+  // accumulators [7][kp] ints after the runtime-sized table
+  constexpr bool BLOCK_ACC = !PRIVATE && ATOM;
+  int4* s_acc = reinterpret_cast<int4*>(smem_raw + (KT > 0 ? 0 : tab_smem_bytes(BLOCK_ACC ? kp : pad32(KCAP))));
+  if (!CT_SMALL) tab_to_smem(const_cast<CentRec*>(s_tab), J.tab, kp, tid, THREADS);
+  const unsigned int CSTRIDE = BLOCK_ACC ? kp : (unsigned int)(KCAP > 0 ? KCAP : 1) * THREADS;
   if (PRIVATE) {
 #pragma unroll 4
     for (int c = 0; c < KCAP; ++c) s_acc[c * THREADS + tid] = make_int4(0, 0, 0, 0);
   }
+  if (BLOCK_ACC)
+    for (unsigned int c = tid; c < 7 * kp; c += THREADS) reinterpret_cast<int*>(s_acc)[c] = 0;
   const float lmax = st->lmax, cmax = st->cmax;
   __syncthreads();
 
@@ -947,6 +988,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
   unsigned int since_flush = 0;
   unsigned int slow = 0;
 
+  // block accumulators: all threads of the block call this together
+  auto flush_block = [&]() {
+    if (!BLOCK_ACC) return;
+    __syncthreads();
+    int* a = reinterpret_cast<int*>(s_acc);
+    for (unsigned int c = tid; c < k; c += THREADS) {
+      const int cnt = a[c + 6 * CSTRIDE];
+      if (cnt != 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const long long v = (long long)a[c + (2 * q + 1) * CSTRIDE] * 4096 + (long long)(unsigned int)a[c + 2 * q * CSTRIDE];
+          atomicAdd(g_acc + c * 4 + q, (unsigned long long)v);
+        }
+        atomicAdd(g_acc + c * 4 + 3, (unsigned long long)(unsigned int)cnt);
+      }
+#pragma unroll
+      for (int q = 0; q < 7; ++q) a[c + q * CSTRIDE] = 0;
+    }
+    __syncthreads();
+    since_flush = 0;
+  };
   auto flush = [&]() {
     if (!PRIVATE) return;
     // Every warp folds the private slots of its own 32 threads for all clusters (no block sync
@@ -987,11 +1049,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     for (; tile < full_tiles; tile += gridDim.x) {
       const unsigned long long next = tile + gridDim.x;
       if (next < full_tiles) lloyd_load<THREADS, P, false>(work, next * TILE + tid, n, nxt);
-      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, cur, tile * TILE + tid, n,
-                                                           k, lmax, cmax, tid, slow);
+      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT, ATOM>(s_tab, x_tab, ctab_big, kp, s_acc, CSTRIDE, g_acc, cur,
+                                                           tile * TILE + tid, n, k, lmax, cmax, tid, slow);
       since_flush += P;
       // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
       if (PRIVATE && since_flush + P > 240) flush();
+      // block accumulators: 2^19 pixels of the block (since_flush counts pixels per thread)
+      if (BLOCK_ACC && (since_flush + P) * THREADS > (1u << 19)) flush_block();
 #pragma unroll
       for (int i = 0; i < P; ++i) cur[i] = nxt[i];
     }
@@ -1001,10 +1065,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     if (PRIVATE && since_flush + P > 240) flush();
     float4 tail[P];
     lloyd_load<THREADS, P, true>(work, full_tiles * TILE + tid, n, tail);
-    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, tail,
+    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT, ATOM>(s_tab, x_tab, ctab_big, kp, s_acc, CSTRIDE, g_acc, tail,
                                                         full_tiles * TILE + tid, n, k, lmax, cmax, tid, slow);
   }
   flush();
+  flush_block();
   if (slow) atomicAdd(&st->slow_pixels, (unsigned long long)slow);
 
   __threadfence();

@@ -1,6 +1,10 @@
 set -x
 mkdir -p gpurun_out
-python tools/sweep_lloyd8.py ${SWEEP:-0,8,9,10} 8192 50 > gpurun_out/sweep_lloyd8.log 2>&1
-cat gpurun_out/sweep_lloyd8.log
-KMG_LLOYD8_VARIANT=${TESTV:-8} timeout 600 python -m pytest tests -m gpu -x -q -k "not 16m and not all_16m" 2>&1 | tail -5 > gpurun_out/gpu_tests_v.log
-cat gpurun_out/gpu_tests_v.log
+for c in 0 1; do
+KMG_LLOYDG_BLOCKACC=$c python tools/prof_lloyd.py 256 8192 6
+KMG_LLOYDG_BLOCKACC=$c python tools/prof_lloyd.py 64 8192 6
+KMG_LLOYDG_BLOCKACC=$c python tools/prof_lloyd.py 1024 4096 4
+done > gpurun_out/lloydg.log 2>&1
+cat gpurun_out/lloydg.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/gpu_tests.log
+cat gpurun_out/gpu_tests.log
