@@ -299,7 +299,7 @@ def run_ours(args):
                        "k": K_CLUSTERS, "bytes_per_px": BYTES_PER_PX, "l2": "work plane 1 GiB per GPU > 126 MB L2",
                        "exact_path_pixels_per_pass": stats["slow_pixels"] / max(stats["passes"], 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd<KT=8,KCAP=8,256 threads,4 px/thread,private accumulators,2 blocks/SM>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd<KT=8,KCAP=8,256 threads,4 px/thread,thread-private atomic slots,2 blocks/SM,table in the constant bank>",
                          "kernel_ms": step_ms},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": K_CLUSTERS * 16 + 64,
