@@ -227,6 +227,16 @@ struct kmg_ctx {
   bool big_block_acc = true;   // KMG_LLOYDG_BLOCKACC=0: accumulate through L2 atomics instead of shared memory
 };
 
+// Ownership of one slot of the constant-bank tables (c_tab / c_tab_big).  Copies of a job (the
+// per-chunk copies of a batched remap) do not own the slot: the copy constructor leaves it empty.
+struct CSlot {
+  int slot = -1, big = 0, device = 0;
+  CSlot() = default;
+  CSlot(const CSlot&) {}
+  CSlot& operator=(const CSlot&) { return *this; }
+  ~CSlot();
+};
+
 struct kmg_job {
   kmg_ctx* ctx = nullptr;
   JobPtrs P{};
@@ -245,10 +255,10 @@ struct kmg_job {
   uint32_t global_w = 0, global_h = 0, row_offset = 0;
   float* d_xfer = nullptr;  // 4 floats, colour broadcast during distributed init
   uint32_t xchg_base = 0;   // PeerXchg::seq_base of this job
-  // slot of the constant-bank table (k <= 8 passes), taken at the first pass, returned with the job
-  int cslot = -1;
+  // slot of the constant-bank table (small-k passes), taken at the first pass, returned with the job
+  CSlot cs_owner;
+  int cslot = -1;  // == cs_owner.slot once acquired; plain copy so that copies of the job can launch with it
   bool cslot_tried = false;
-  ~kmg_job();
 };
 
 // The constant bank belongs to the device (one copy of the module per device), not to a context:
@@ -256,7 +266,8 @@ struct kmg_job {
 static std::mutex g_cslot_mu;
 static std::vector<int> g_cslots_free[2][64];  // [small | big tables][device]
 static bool g_cslots_ready[2][64];
-static int cslot_acquire(kmg_ctx* ctx, bool big = false) {
+static int cslot_acquire(kmg_job* j, bool big = false) {
+  kmg_ctx* ctx = j->ctx;
   if (!ctx->c_tab_dev || ctx->device >= 64) return -1;
   std::lock_guard<std::mutex> g(g_cslot_mu);
   std::vector<int>& fl = g_cslots_free[big][ctx->device];
@@ -267,14 +278,17 @@ static int cslot_acquire(kmg_ctx* ctx, bool big = false) {
   if (fl.empty()) return -1;
   int s = fl.back();
   fl.pop_back();
+  j->cs_owner.slot = s;
+  j->cs_owner.big = big ? 1 : 0;
+  j->cs_owner.device = ctx->device;
   return s;
 }
 // Jobs are only dropped after the work they enqueued has been waited for (every blocking entry
 // point synchronises; kmg_job_destroy frees device memory first, which synchronises the device).
-kmg_job::~kmg_job() {
-  if (cslot >= 0 && ctx) {
+CSlot::~CSlot() {
+  if (slot >= 0) {
     std::lock_guard<std::mutex> g(g_cslot_mu);
-    g_cslots_free[k > 32 ? 1 : 0][ctx->device].push_back(cslot);
+    g_cslots_free[big][device].push_back(slot);
   }
 }
 
@@ -691,7 +705,7 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
     if (LLOYD_VARIANTS[v].const_tab) {
       if (j->cslot < 0 && !j->cslot_tried) {
         j->cslot_tried = true;
-        j->cslot = cslot_acquire(ctx);
+        j->cslot = cslot_acquire(j);
       }
       if (j->cslot < 0) v = ctx->lloyd_nocst[cls];  // no free slot in the constant bank: shared-memory table
     }
@@ -706,7 +720,7 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
     int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
     if (j->k <= (uint32_t)CTAB_BIG_K && ctx->big_const && !ctx->big_block_acc && j->cslot < 0 && !j->cslot_tried) {
       j->cslot_tried = true;
-      j->cslot = cslot_acquire(ctx, true);
+      j->cslot = cslot_acquire(j, true);
     }
     if (j->k <= LLOYDGS_MAX_K && ctx->big_block_acc) {
       smem += (size_t)7 * pad32(j->k) * 4;
@@ -1292,12 +1306,68 @@ extern "C" int kmg_kmeans_palette(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w,
   return KMG_OK;
 }
 
+// Remap of one large host image as a pipeline of row bands over three workspaces (stream + buffers
+// each): the upload of band i+1 and the read-back of band i-1 overlap the kernel of band i, so the
+// call costs about one direction of PCIe traffic instead of upload + kernel + read-back in series.
+// Bands start on rows that are multiples of 4, which keeps the 4x4 dither matrix aligned
+// (mix_colors.wgsl:21-27 indexes it with x % 4 + 4 (y % 4)); every pixel is independent otherwise.
+// Overlap needs page-locked caller buffers; pageable ones still work, the copies then serialise.
+static int remap_banded(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, const float* centroids, uint32_t k,
+                        int cs, int mode, uint8_t* out_rgba) {
+  const size_t row_bytes = (size_t)w * 4;
+  const size_t total = row_bytes * h;
+  size_t band_bytes = std::min<size_t>((size_t)16 << 20, std::max<size_t>((size_t)4 << 20, total / 8));
+  uint32_t band_rows = (uint32_t)std::max<size_t>(4, (band_bytes / row_bytes) & ~(size_t)3);
+  const uint32_t n_bands = (h + band_rows - 1) / band_rows;
+  Workspace* wss[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t prepared = nullptr;
+  int rc = KMG_OK;
+  for (int i = 0; i < 3 && rc == KMG_OK; ++i) {
+    wss[i] = ws_acquire(ctx);
+    if (!wss[i]) rc = fail(KMG_ERR_CUDA, "could not create a workspace");
+  }
+  auto run = [&]() -> int {
+    CU(cudaEventCreateWithFlags(&prepared, cudaEventDisableTiming));
+    TRY(wss[0]->blob.ensure(job_blob_bytes(k)));
+    kmg_job job;
+    kmg_opts o;
+    kmg_default_opts(&o);
+    TRY(job_setup(&job, ctx, nullptr, w, h, k, cs, o, wss[0]->blob.p, nullptr, wss[0]->h_state, wss[0]->stream));
+    CU(cudaMemcpyAsync(job.P.cent, centroids, (size_t)k * 16, cudaMemcpyHostToDevice, wss[0]->stream));
+    TRY(launch_prepare(&job, true, wss[0]->stream));
+    CU(cudaEventRecord(prepared, wss[0]->stream));
+    CU(cudaStreamWaitEvent(wss[1]->stream, prepared, 0));
+    CU(cudaStreamWaitEvent(wss[2]->stream, prepared, 0));
+    for (uint32_t b = 0; b < n_bands; ++b) {
+      Workspace* ws = wss[b % 3];
+      const uint32_t r0 = b * band_rows, rows = std::min(band_rows, h - r0);
+      const size_t bytes = row_bytes * rows, off = row_bytes * r0;
+      TRY(ws->in.ensure(row_bytes * band_rows));
+      TRY(ws->out.ensure(row_bytes * band_rows));
+      CU(cudaMemcpyAsync(ws->in.p, rgba + off, bytes, cudaMemcpyHostToDevice, ws->stream));
+      TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, rows, mode, (uint8_t*)ws->out.p, ws->stream, true));
+      CU(cudaMemcpyAsync(out_rgba + off, ws->out.p, bytes, cudaMemcpyDeviceToHost, ws->stream));
+    }
+    for (int i = 0; i < 3; ++i) CU(cudaStreamSynchronize(wss[i]->stream));
+    return KMG_OK;
+  };
+  if (rc == KMG_OK) rc = run();
+  for (int i = 0; i < 3; ++i)
+    if (wss[i]) {
+      if (rc != KMG_OK) cudaStreamSynchronize(wss[i]->stream);
+      ws_release(ctx, wss[i]);
+    }
+  if (prepared) cudaEventDestroy(prepared);
+  return rc;
+}
+
 extern "C" int kmg_remap(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, const float* centroids, uint32_t k,
                          int cs, int mode, uint8_t* out_rgba) {
   TRY(check_image_args("kmg_remap", ctx, rgba, w, h, k, cs));
   if (!centroids || !out_rgba) return fail(KMG_ERR_BAD_ARG, "kmg_remap: NULL argument");
   if (mode < KMG_REPLACE || mode > KMG_MELD) return fail(KMG_ERR_BAD_ARG, "kmg_remap: unknown mode %d", mode);
   CU(cudaSetDevice(ctx->device));
+  if ((size_t)w * h * 4 >= ((size_t)12 << 20) && h >= 12) return remap_banded(ctx, rgba, w, h, centroids, k, cs, mode, out_rgba);
   Workspace* ws = ws_acquire(ctx);
   if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
   WsGuard guard{ctx, ws};

@@ -506,6 +506,59 @@ def test_concurrent_callers(proc, K, oracle, tokyo):
         assert passes == opasses and np.array_equal(bits(cent), bits(ocent)) and np.array_equal(out.rgba, want)
 
 
+def test_remap_of_a_large_host_image_runs_as_row_bands(proc, K, oracle):
+    """kmg_remap pipelines host images >= 12 MiB as row bands over three streams (upload / kernel /
+    read-back overlap).  Ragged geometry: width not a multiple of 4, rows not a multiple of the
+    band height; the dither matrix must stay aligned across band boundaries."""
+    w, h = 2021, 1667  # 13.5 MB -> four bands of 416 rows + a short one
+    img = oracle.synth(w * h, seed=11, blobs=6).reshape(h, w, 4)
+    pal = np.array([[12, 16, 20, 255], [200, 40, 30, 255], [240, 240, 230, 255], [30, 120, 200, 255], [90, 160, 60, 255]],
+                   np.uint8)
+    for mode, name in ((K.ReduceMode.Replace, "replace"), (K.ReduceMode.Dither, "dither"), (K.ReduceMode.Meld, "meld")):
+        got = proc.find(img, pal, mode)
+        want = oracle.find(img, pal, name)
+        assert np.array_equal(got.rgba, want), name
+    # pinned buffers (the overlapping case) give the same bytes
+    pin_in = K.pinned_empty((h, w, 4))
+    pin_in[...] = img
+    pin_out = K.pinned_empty((h, w, 4))
+    got = proc.find(pin_in, pal, K.ReduceMode.Dither, out=pin_out)
+    assert np.array_equal(pin_out, oracle.find(img, pal, "dither"))
+
+
+def test_concurrent_staged_jobs_share_the_constant_bank(proc, K, oracle, tokyo):
+    """Staged launches (no shrink, > 65,536 clustered pixels) with k <= 16 keep their table in a
+    per-job slot of the constant bank: jobs running at the same time on different streams must not
+    see each other's tables, and a reduce() (whose remap copies the job) must hand its slot back
+    exactly once.  20 threads x 3 rounds; every result against the sequential call, one against
+    the oracle."""
+    img = np.ascontiguousarray(tokyo[:300, :400])
+    opts = K.Opts(max_dim=0, max_iter=12)
+    ks = [3, 5, 8, 8, 9, 12, 16, 16, 7, 4] * 2
+    seq = {k: proc.reduce(k, img, reduce_mode=K.ReduceMode.Dither, opts=opts, return_details=True) for k in set(ks)}
+    errors = []
+
+    def work(i, k):
+        for _ in range(3):
+            out, cent, passes = proc.reduce(k, img, reduce_mode=K.ReduceMode.Dither, opts=opts, return_details=True)
+            sout, scent, spasses = seq[k]
+            if passes != spasses or not np.array_equal(bits(cent), bits(scent)) or not np.array_equal(out.rgba, sout.rgba):
+                errors.append((i, k))
+
+    threads = [threading.Thread(target=work, args=(i, k)) for i, k in enumerate(ks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    want, ocent, opasses = oracle.reduce(img, 8, "dither", oracle.default_opts(max_dim=0, max_iter=12))
+    out, cent, passes = seq[8]
+    assert passes == opasses and np.array_equal(bits(cent), bits(ocent)) and np.array_equal(out.rgba, want)
+    # far more sequential jobs than slots (64): slots must come back
+    for _ in range(80):
+        proc.kmeans_centroids(6, img, opts=K.Opts(max_dim=0, max_iter=2))
+
+
 # ---- the certificate --------------------------------------------------------------------------------
 
 def test_fast_lab_error_bound(proc, D):
