@@ -900,28 +900,46 @@ static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cud
   }
 #endif
   const int grid = grid_for(ctx, n, 256 * 4, 8);
+  // single GPU: the round's last block resolves the winner (PICK 1); sharded with peer mailboxes:
+  // arg-max and colour travel inside the round's launch (PICK 2); sharded over NCCL: PICK 0 + k_init_pick
+  const bool fused = dist && ctx->p2p;
+  const PeerXchg X = peer_xchg(ctx, j, fused);
   for (uint32_t c = 1; c < j->k; ++c) {
+    if (!dist) {
+      if (c == 1)
+        k_init_round<true, 1><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
+      else
+        k_init_round<false, 1><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
+      LAUNCHED(ctx);
+      CHECK_LAUNCH();
+      continue;
+    }
+    if (fused) {
+      if (c == 1)
+        k_init_round<true, 2><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
+      else
+        k_init_round<false, 2><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
+      LAUNCHED(ctx);
+      CHECK_LAUNCH();
+      continue;
+    }
     if (c == 1)
-      k_init_round<true><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c);
+      k_init_round<true, 0><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
     else
-      k_init_round<false><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c);
+      k_init_round<false, 0><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
     LAUNCHED(ctx);
     CHECK_LAUNCH();
 #if KMG_HAVE_NCCL_HEADER
-    if (dist) {
-      NC(nccl_api().AllReduce(j->P.keys + c, j->P.keys + c, 1, ncclUint64, ncclMax, ctx->comm, s));
-      CU(cudaMemsetAsync(j->d_xfer, 0, 16, s));
-      CU(cudaMemsetAsync(j->P.cent + c, 0, 16, s));
-    }
+    NC(nccl_api().AllReduce(j->P.keys + c, j->P.keys + c, 1, ncclUint64, ncclMax, ctx->comm, s));
+    CU(cudaMemsetAsync(j->d_xfer, 0, 16, s));
+    CU(cudaMemsetAsync(j->P.cent + c, 0, 16, s));
 #endif
     k_init_pick<<<1, 32, 0, s>>>(j->P, j->work, n, offset, c);
     LAUNCHED(ctx);
     CHECK_LAUNCH();
 #if KMG_HAVE_NCCL_HEADER
-    if (dist) {
-      CU(cudaMemcpyAsync(j->d_xfer, j->P.cent + c, 16, cudaMemcpyDeviceToDevice, s));
-      TRY(share_colour(j, c, s));
-    }
+    CU(cudaMemcpyAsync(j->d_xfer, j->P.cent + c, 16, cudaMemcpyDeviceToDevice, s));
+    TRY(share_colour(j, c, s));
 #endif
   }
   TRY(launch_prepare(j, false, s));

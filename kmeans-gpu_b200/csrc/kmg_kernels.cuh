@@ -658,12 +658,21 @@ __global__ void k_init_seed(JobPtrs J, const float4* __restrict__ work, unsigned
 }
 
 // pixel_offset: global index of this shard's first pixel (0 on a single GPU).
-template <bool FIRST>
+// PICK 0: only the arg-max key is produced (k_init_pick resolves it; NCCL path of a sharded image).
+// PICK 1: the last block to finish resolves the winner into centroid j itself (single GPU).
+// PICK 2: sharded image with peer mailboxes — the last block on every GPU posts its local winner
+//   (key, global pixel index, colour) to every rank's mailbox over NVLink, waits for the peers'
+//   flags, and every rank takes the colour of the largest key: the arg-max all-reduce and the
+//   colour broadcast of the round happen inside the round's own launch (no NCCL, no extra launch).
+//   Parity (k - j) & 1 alternates down to the first Lloyd pass (parity 0); flags carry
+//   seq_base - j, disjoint from the passes' seq_base + pass + 1.
+template <bool FIRST, int PICK>
 __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __restrict__ work,
                                                     float* __restrict__ dmin, unsigned long long n,
-                                                    unsigned long long pixel_offset, unsigned int j) {
+                                                    unsigned long long pixel_offset, unsigned int j, PeerXchg X) {
   __shared__ unsigned long long s_key[8];
-  // centroid j-1 was resolved into J.cent[j-1] by k_init_pick (or k_init_seed for j == 1).
+  __shared__ bool s_last;
+  // centroid j-1 was resolved into J.cent[j-1] by the previous round (or k_init_seed for j == 1).
   const float4 c = J.cent[j - 1];
   const float cc = ex::chroma(c.y, c.z);
   unsigned long long best = 0ull;
@@ -683,6 +692,92 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) best = s_key[w] > best ? s_key[w] : best;
     atomicMax(J.keys + j, best);
+  }
+  if (PICK == 0) return;
+  // the last block resolves the round
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&J.st->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __shared__ unsigned int s_fault;
+  if (threadIdx.x == 0) s_fault = 0;
+  __syncthreads();
+  unsigned long long key = 0ull, pix = 0ull;
+  float4 col = make_float4(0.f, 0.f, 0.f, 1.0f);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    key = __ldcg(J.keys + j);
+    pix = key_to_pixel(key);
+    if (pix >= pixel_offset && pix - pixel_offset < n) {
+      const float4 v = work[pix - pixel_offset];
+      col = make_float4(v.x, v.y, v.z, 1.0f);
+    } else {
+      pix = ~0ull;  // zero maximum on a shard that does not hold pixel 0: no candidate
+    }
+  }
+  if (PICK == 2) {
+    const unsigned int k = J.st->k;
+    const unsigned int par = (k - j) & 1u;
+    const unsigned int seq = X.seq_base - j;
+    if (threadIdx.x == 0) {
+      const size_t slot = ((size_t)par * MAX_PEERS + X.rank) * X.xcap;
+      for (unsigned int r = 0; r < X.n_ranks; ++r) {
+        longlong2* dst = reinterpret_cast<longlong2*>(X.mbox[r] + slot);
+        dst[0] = make_longlong2((long long)key, (long long)pix);
+        dst[1] = make_longlong2((long long)(((unsigned long long)__float_as_uint(col.y) << 32) | __float_as_uint(col.x)),
+                                (long long)__float_as_uint(col.z));
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < X.n_ranks) {
+      volatile unsigned int* theirs = X.flags[threadIdx.x] + par * MAX_PEERS + X.rank;
+      *theirs = seq;
+      volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + threadIdx.x;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*mine != seq) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {  // 4 s: a peer never launched this round
+          s_fault = 1;
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_fault) {
+        J.st->conv = PASS_FAULT;
+        J.st->done = 1;
+      } else {
+        // largest key over the ranks (keys of different shards never tie: they embed the global
+        // pixel index; all-zero maxima resolve to global pixel 0), colour from the rank that holds it
+        unsigned long long kmax = 0ull;
+        for (unsigned int r = 0; r < X.n_ranks; ++r) {
+          const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap;
+          const unsigned long long kr = (unsigned long long)a[0];
+          kmax = kr > kmax ? kr : kmax;
+        }
+        const unsigned long long want = key_to_pixel(kmax);
+        for (unsigned int r = 0; r < X.n_ranks; ++r) {
+          const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap;
+          if ((unsigned long long)a[1] == want) {
+            const unsigned long long la = (unsigned long long)a[2];
+            col = make_float4(__uint_as_float((unsigned int)la), __uint_as_float((unsigned int)(la >> 32)),
+                              __uint_as_float((unsigned int)(unsigned long long)a[3]), 1.0f);
+          }
+        }
+        key = kmax;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    J.cent[j] = col;
+    J.keys[j] = key;
+    J.st->ticket = 0;
   }
 }
 
