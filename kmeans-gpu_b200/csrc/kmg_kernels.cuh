@@ -676,15 +676,36 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
   const float4 c = J.cent[j - 1];
   const float cc = ex::chroma(c.y, c.z);
   unsigned long long best = 0ull;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    float4 v = ldg_stream(work + p);
-    float d = ex::cie94_c(v.x, v.y, v.z, v.w, c.x, c.y, c.z, cc);
-    float dm = FIRST ? fminf(1000000.0f, d) : fminf(dmin[p], d);  // kmeans++_calc_diff.wgsl:27-31
-    dmin[p] = dm;
-    unsigned long long key =
-        ((unsigned long long)__float_as_uint(dm) << 32) | (((pixel_offset + p) & 0xffffffffull) ^ 15ull);
-    best = key > best ? key : best;
+  // four pixels per thread and step, all eight loads in flight before the first distance is
+  // computed: the round is a latency-bound stream otherwise (one dependent load -> ~100
+  // instructions -> store per pixel)
+  constexpr int U = 4;
+  const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x * U;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x * U + threadIdx.x; base < n; base += step) {
+    float4 v[U];
+    float old[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned long long p = base + (unsigned long long)i * blockDim.x;
+      const bool ok = p < n;
+      v[i] = ok ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      old[i] = (!FIRST && ok) ? dmin[p] : 1000000.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned long long p = base + (unsigned long long)i * blockDim.x;
+      if (p < n) {
+        const float d = ex::cie94_c(v[i].x, v[i].y, v[i].z, v[i].w, c.x, c.y, c.z, cc);
+        // kmeans++_calc_diff.wgsl:27-31 (the first round starts from 1000000.0).  The plane is only
+        // written where the minimum decreases: in round j about 1/j of the pixels, so most 32-byte
+        // sectors of the plane stay clean in HBM.
+        const float dm = fminf(old[i], d);
+        if (FIRST || d < old[i]) dmin[p] = dm;
+        const unsigned long long key =
+            ((unsigned long long)__float_as_uint(dm) << 32) | (((pixel_offset + p) & 0xffffffffull) ^ 15ull);
+        best = key > best ? key : best;
+      }
+    }
   }
   best = warp_max_u64(best);
   if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = best;
