@@ -180,9 +180,15 @@ struct Buf {
 
 struct Workspace {
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // created on first use: uploads that overlap kernels on `stream`
+  std::vector<cudaEvent_t> band_done;  // one per band in flight (banded upload + convert)
   Buf in, out, small, work, dmin, blob;
   JobState* h_state = nullptr;  // pinned
   void release() {
+    for (cudaEvent_t e : band_done) cudaEventDestroy(e);
+    band_done.clear();
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr;
     in.release();
     out.release();
     small.release();
@@ -1265,8 +1271,45 @@ static int kmeans_small_on_device(kmg_ctx* ctx, const SmallPlan& plan, const uin
 // What k_kmeans_small leaves in the blob besides the centroids (SmallParams::tail) for a remap mode.
 static int tail_for_mode(int mode) { return mode == KMG_DITHER ? 2 : (mode == KMG_REPLACE ? 1 : 0); }
 
+// Upload of a host image into ws->in.  Large images that will be clustered at full size by the
+// staged launches (no shrink, too large for the fused kernel) are uploaded in 16 MiB bands on a
+// second stream, and every band is converted to the work plane as soon as it has arrived, so the
+// conversion hides behind the upload (*plane_ready: ws->work already holds the plane).
+static int upload_image(kmg_ctx* ctx, Workspace* ws, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t k, int cs,
+                        const kmg_opts& o, bool* plane_ready) {
+  const size_t n = (size_t)w * h, bytes = n * 4;
+  *plane_ready = false;
+  TRY(ws->in.ensure(bytes));
+  const bool shrink = o.max_dim != 0 && (w > o.max_dim || h > o.max_dim);
+  SmallPlan plan;
+  const bool fused = !(o.flags & KMG_OPT_NO_FUSED_KMEANS) && small_plan(ctx, n, k, 1, &plan);
+  if (shrink || fused || bytes < ((size_t)32 << 20)) {
+    CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, ws->stream));
+    return KMG_OK;
+  }
+  if (!ws->copy_stream) CU(cudaStreamCreateWithFlags(&ws->copy_stream, cudaStreamNonBlocking));
+  TRY(ws->work.ensure(n * 16));
+  const size_t band_px = ((size_t)16 << 20) / 4;
+  const size_t n_bands = (n + band_px - 1) / band_px;
+  while (ws->band_done.size() < n_bands) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ws->band_done.push_back(e);
+  }
+  for (size_t b = 0; b < n_bands; ++b) {
+    const size_t p0 = b * band_px, np = std::min(band_px, n - p0);
+    CU(cudaMemcpyAsync((uint8_t*)ws->in.p + p0 * 4, rgba + p0 * 4, np * 4, cudaMemcpyHostToDevice, ws->copy_stream));
+    CU(cudaEventRecord(ws->band_done[b], ws->copy_stream));
+    CU(cudaStreamWaitEvent(ws->stream, ws->band_done[b], 0));
+    TRY(launch_convert(ctx, (const uint8_t*)ws->in.p + p0 * 4, np, cs, (float*)ws->work.p + p0 * 4, ws->stream));
+  }
+  *plane_ready = true;
+  return KMG_OK;
+}
+
 static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, uint32_t w, uint32_t h, uint32_t k,
-                            int cs, const kmg_opts& o, kmg_job* job, bool* prepared, int tail = 0) {
+                            int cs, const kmg_opts& o, kmg_job* job, bool* prepared, int tail = 0,
+                            bool plane_ready = false) {
   cudaStream_t s = ws->stream;
   uint32_t iw = w, ih = h;
   const bool shrink = o.max_dim != 0 && (w > o.max_dim || h > o.max_dim);  // structures.rs:67-74
@@ -1289,7 +1332,7 @@ static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, 
   }
   TRY(ws->work.ensure(n * 16));
   TRY(ws->dmin.ensure(n * 4));
-  TRY(launch_convert(ctx, img, n, cs, (float*)ws->work.p, s));
+  if (!plane_ready) TRY(launch_convert(ctx, img, n, cs, (float*)ws->work.p, s));
   TRY(job_setup(job, ctx, (const float*)ws->work.p, iw, ih, k, cs, o, ws->blob.p, (float*)ws->dmin.p, ws->h_state, s));
   TRY(job_init_impl(job, nullptr, nullptr, s));
   TRY(job_run_impl(job, nullptr, s));
@@ -1313,11 +1356,11 @@ extern "C" int kmg_kmeans_palette(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w,
   Workspace* ws = ws_acquire(ctx);
   if (!ws) return fail(KMG_ERR_CUDA, "could not create a workspace");
   WsGuard guard{ctx, ws};
-  const size_t bytes = (size_t)w * h * 4;
-  TRY(ws->in.ensure(bytes));
-  CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, ws->stream));
+  const kmg_opts o = resolve_opts(opts);
+  bool plane_ready = false;
+  TRY(upload_image(ctx, ws, rgba, w, h, k, cs, o, &plane_ready));
   kmg_job job;
-  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, nullptr));
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, o, &job, nullptr, 0, plane_ready));
   CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, ws->stream));
   CU(cudaStreamSynchronize(ws->stream));
   if (passes_out) *passes_out = ws->h_state->passes;
@@ -1417,12 +1460,13 @@ extern "C" int kmg_reduce(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_
   WsGuard guard{ctx, ws};
   cudaStream_t s = ws->stream;
   const size_t bytes = (size_t)w * h * 4;
-  TRY(ws->in.ensure(bytes));
   TRY(ws->out.ensure(bytes));
-  CU(cudaMemcpyAsync(ws->in.p, rgba, bytes, cudaMemcpyHostToDevice, s));
+  const kmg_opts o = resolve_opts(opts);
+  bool plane_ready = false;
+  TRY(upload_image(ctx, ws, rgba, w, h, k, cs, o, &plane_ready));
   kmg_job job;
   bool prepared = false;
-  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, resolve_opts(opts), &job, &prepared, tail_for_mode(mode)));
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, o, &job, &prepared, tail_for_mode(mode), plane_ready));
   TRY(launch_remap(&job, (const uint8_t*)ws->in.p, w, h, mode, (uint8_t*)ws->out.p, s, prepared));
   CU(cudaMemcpyAsync(out_rgba, ws->out.p, bytes, cudaMemcpyDeviceToHost, s));
   if (centroids_out) CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, s));

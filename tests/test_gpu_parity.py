@@ -526,6 +526,19 @@ def test_remap_of_a_large_host_image_runs_as_row_bands(proc, K, oracle):
     assert np.array_equal(pin_out, oracle.find(img, pal, "dither"))
 
 
+def test_banded_upload_of_a_large_unshrunk_image(proc, K, oracle):
+    """Host images >= 32 MiB that are clustered at full size are uploaded in bands on a second
+    stream and converted band by band (the conversion hides behind the upload)."""
+    w, h = 3001, 2803  # 33.6 MB, ragged against the 16 MiB bands
+    img = oracle.synth(w * h, seed=21, blobs=8).reshape(h, w, 4)
+    opts = K.Opts(max_dim=0, max_iter=3, check_every=0)
+    cent, passes = proc.kmeans_centroids(4, img, opts=opts)
+    ocent, opasses = oracle.kmeans(img, 4, oracle.LAB, oracle.default_opts(max_dim=0, max_iter=3, check_every=0))
+    assert passes == opasses and np.array_equal(bits(cent), bits(ocent))
+    out = proc.reduce(4, img, reduce_mode=K.ReduceMode.Replace, opts=opts)
+    assert np.array_equal(out.rgba, oracle.remap_replace(img, ocent))
+
+
 def test_concurrent_staged_jobs_share_the_constant_bank(proc, K, oracle, tokyo):
     """Staged launches (no shrink, > 65,536 clustered pixels) with k <= 16 keep their table in a
     per-job slot of the constant bank: jobs running at the same time on different streams must not

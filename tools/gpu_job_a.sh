@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-python tools/prof_init.py 64 8192
-python tools/prof_init.py 256 8192
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 300 --warmup 5 > gpurun_out/b1.json 2> gpurun_out/b1.err; python -c "
+import json; d=json.load(open('gpurun_out/b1.json')); print(d['value'], d['roofline']['frac'], d['e2e'], d['extras']['config4_8192_k256_sharded']['init_ms'])"; tail -2 gpurun_out/b1.err
