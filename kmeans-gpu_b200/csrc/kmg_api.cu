@@ -307,7 +307,7 @@ static void p2p_teardown(kmg_ctx* ctx);
 // global-reduction kernel adds 4 values per pixel, so every resident block gets its own copy
 // (bounded to 8 MiB) and same-address serialisation in L2 disappears.
 static uint32_t job_acc_copies(uint32_t k) {
-  if (k <= 32) return 8;
+  if (k <= 2048) return 8;  // private slots / block accumulators: one drain per block, folded by the last block
   size_t cap = ((size_t)8 << 20) / ((size_t)k * 32);
   return (uint32_t)std::max<size_t>(8, std::min<size_t>(304, cap));
 }

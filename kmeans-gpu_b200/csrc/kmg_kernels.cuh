@@ -203,6 +203,10 @@ __device__ void build_table(const JobPtrs& J, unsigned int k, int color_space, b
     }
     J.st->lmax = lmax;
     J.st->cmax = cmax;
+  }
+  // Only the remap needs the dither threshold (k_prepare passes want_palette): 2 (k - 2) exact
+  // distances walked by one thread have no place in the tail of every Lloyd pass.
+  if (tid == 0 && want_palette) {
     // mix_colors.wgsl:53-68 — greedy farthest pair, asymmetric distance with centroid i first.
     float thr = 0.0f;
     if (k > 1) {
