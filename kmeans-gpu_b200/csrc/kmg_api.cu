@@ -231,6 +231,7 @@ struct kmg_ctx {
   void* c_tab_big_dev = nullptr;
   bool big_const = false;      // KMG_LLOYDG_CONST=1: chunk loop of the k > 32 pass fed from the constant bank (slower)
   bool big_block_acc = true;   // KMG_LLOYDG_BLOCKACC=0: accumulate through L2 atomics instead of shared memory
+  int block_flush_log2 = 19;   // KMG_BLOCKACC_FLUSH_LOG2 (10..19): drain interval of the block accumulators (tests)
 };
 
 // Ownership of one slot of the constant-bank tables (c_tab / c_tab_big).  Copies of a job (the
@@ -574,6 +575,7 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   CU(cudaGetSymbolAddress(&ctx->c_tab_big_dev, c_tab_big));
   if (const char* e = getenv("KMG_LLOYDG_CONST")) ctx->big_const = atoi(e) != 0;
   if (const char* e = getenv("KMG_LLOYDG_BLOCKACC")) ctx->big_block_acc = atoi(e) != 0;
+  if (const char* e = getenv("KMG_BLOCKACC_FLUSH_LOG2")) ctx->block_flush_log2 = std::min(19, std::max(10, atoi(e)));
   CU(cudaFuncSetAttribute(LLOYDGS, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU(cudaFuncSetAttribute(LLOYDGC, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   for (int v = 0; v < N_LLOYD_VARIANTS; ++v) {
@@ -731,7 +733,7 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
     if (j->k <= LLOYDGS_MAX_K && ctx->big_block_acc) {
       smem += (size_t)7 * pad32(j->k) * 4;
       grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
-      LLOYDGS<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0, j->k);
+      LLOYDGS<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, ctx->block_flush_log2, j->k);
     } else if (j->cslot >= 0) {
       CU(cudaMemcpyAsync((char*)ctx->c_tab_big_dev + (size_t)j->cslot * CTAB_BIG_K * 24, j->P.tab,
                          (size_t)pad32(j->k) * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));

@@ -1107,6 +1107,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
   unsigned long long* g_acc = reinterpret_cast<unsigned long long*>(J.acc + (size_t)(blockIdx.x % J.acc_copies) * k * 4);
   unsigned int since_flush = 0;
   unsigned int slow = 0;
+  // block accumulators without a constant-bank table: `cslot` carries log2 of the drain interval in
+  // pixels per block (19 in production: 4095 * 2^19 < 2^31; tests lower it to exercise the drain)
+  const unsigned int block_flush_px = (BLOCK_ACC && !CT) ? (1u << cslot) : (1u << 19);
 
   // block accumulators: all threads of the block call this together
   auto flush_block = [&]() {
@@ -1175,7 +1178,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
       // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
       if (PRIVATE && since_flush + P > 240) flush();
       // block accumulators: 2^19 pixels of the block (since_flush counts pixels per thread)
-      if (BLOCK_ACC && (since_flush + P) * THREADS > (1u << 19)) flush_block();
+      if (BLOCK_ACC && (since_flush + P) * THREADS > block_flush_px) flush_block();
 #pragma unroll
       for (int i = 0; i < P; ++i) cur[i] = nxt[i];
     }

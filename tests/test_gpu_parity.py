@@ -183,7 +183,8 @@ def test_init_picks_with_ties(proc, D, K, oracle, torch, w, h, k):
 
 # ---- K5 + K6/K7 fused pass, Lloyd loop -----------------------------------------------------------
 
-@pytest.mark.parametrize("k,n_side", [(2, 300), (8, 512), (16, 400), (24, 333), (32, 256), (48, 300), (256, 256)])
+@pytest.mark.parametrize("k,n_side", [(1, 64), (2, 300), (8, 512), (9, 200), (16, 400), (24, 333), (32, 256), (48, 300),
+                                      (256, 256), (700, 160), (2100, 128)])
 def test_lloyd_pass_bit_exact(proc, D, K, oracle, torch, k, n_side):
     w = h = n_side
     img = oracle.synth(w * h, seed=k, blobs=2 * k).reshape(h, w, 4)
@@ -205,6 +206,28 @@ def test_lloyd_pass_bit_exact(proc, D, K, oracle, torch, k, n_side):
         assert st["converged"] == oconv
     assert job.stats()["passes"] == 3
     job.close()
+
+
+def test_block_accumulators_drain_mid_pass(K, D, oracle, torch, monkeypatch):
+    """k > 32: block accumulators in shared memory are drained every 2^19 pixels per block in
+    production; with the interval lowered to 2^11 every block drains many times in one pass."""
+    monkeypatch.setenv("KMG_BLOCKACC_FLUSH_LOG2", "11")
+    p = K.ImageProcessor(0)
+    try:
+        k, w, h = 40, 1400, 900
+        img = oracle.synth(w * h, seed=9, blobs=80).reshape(h, w, 4)
+        lab = oracle.convert(img)
+        work = D.convert(p, dev_rgba(torch, img))
+        cent = lab[np.random.default_rng(9).choice(w * h, k, replace=False)].copy()
+        cent[:, 3] = 1.0
+        job = D.Job(p, work, w, h, k)
+        job.set_centroids(cent)
+        job.step(1)
+        labels = oracle.assign(lab, cent)
+        assert np.array_equal(job.sums(), oracle.partial_sums(lab, labels, k))
+        job.close()
+    finally:
+        p.close()
 
 
 def test_lloyd_empty_cluster_keeps_centroid(proc, D, K, oracle, torch):
@@ -545,8 +568,11 @@ def test_concurrent_staged_jobs_share_the_constant_bank(proc, K, oracle, tokyo):
     see each other's tables, and a reduce() (whose remap copies the job) must hand its slot back
     exactly once.  20 threads x 3 rounds; every result against the sequential call, one against
     the oracle."""
-    img = np.ascontiguousarray(tokyo[:300, :400])
+    img = np.ascontiguousarray(tokyo[:480, :640])  # 307,200 px: beyond what the one-launch k-means holds
     opts = K.Opts(max_dim=0, max_iter=12)
+    n0 = proc.launch_count()
+    proc.kmeans_centroids(8, img, opts=K.Opts(max_dim=0, max_iter=2))
+    assert proc.launch_count() - n0 >= 10  # really the staged launches (convert, seed, 7 rounds, prepare, passes)
     ks = [3, 5, 8, 8, 9, 12, 16, 16, 7, 4] * 2
     seq = {k: proc.reduce(k, img, reduce_mode=K.ReduceMode.Dither, opts=opts, return_details=True) for k in set(ks)}
     errors = []
