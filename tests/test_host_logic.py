@@ -155,3 +155,30 @@ def test_synth_generator_is_stable(oracle):
     whole = oracle.synth(1000, seed=3, blobs=32, frame=7)
     parts = np.concatenate([oracle.synth(400, seed=3, blobs=32, frame=7), oracle.synth(600, first_pixel=400, seed=3, blobs=32, frame=7)])
     assert np.array_equal(whole, parts)
+
+
+def test_header_is_plain_c_and_links(native_lib, tmp_path):
+    """The boundary is a C ABI: include/kmeans_gpu.h must compile as C99 (no C++ in the signatures)
+    and a plain C caller must link against the library (host-only entry points run without a GPU)."""
+    import subprocess
+
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include "kmeans_gpu.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "  kmg_opts o; kmg_default_opts(&o);\n"
+        "  uint32_t w = 0, h = 0; kmg_resized_dims(768, 513, o.max_dim, &w, &h);\n"
+        "  uint8_t px[8] = {10, 10, 10, 255, 250, 250, 250, 255}, pal[8]; uint32_t n = 0;\n"
+        "  int rc = kmg_octree_palette(px, 2, 2, pal, &n);\n"
+        "  float lab[8]; kmg_fixed_centroids(pal, n, KMG_LAB, lab);\n"
+        '  printf("%u %u %u %d %d %.3f\\n", w, h, n, rc, kmg_abi_version(), lab[0]);\n'
+        "  return 0;\n"
+        "}\n")
+    lib_dir = ROOT / "kmeans-gpu_b200" / "lib"
+    exe = tmp_path / "caller"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o",
+                           str(exe), f"-L{lib_dir}", "-lkmeans_gpu", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[:5] == ["256", "171", "2", "0", "1"]
+    assert abs(float(out[5]) - 2.742) < 0.01  # L of #0a0a0a
