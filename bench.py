@@ -388,7 +388,30 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
     for _ in range(reps):
         proc.palette(8, tk)
     t_pal = (time.perf_counter() - t0) / reps
+    # the reference's own concurrency pattern: 14 host threads share one ImageProcessor
+    # (core/examples/parallel.rs:23,36-51); every thread reduces with its own pinned buffers
+    n_thr, per_thr = 14, 30
+    bufs = []
+    for _ in range(n_thr):
+        bi, bo = K.pinned_empty(tokyo.shape), K.pinned_empty(tokyo.shape)
+        bi[...] = tokyo
+        bufs.append((bi, bo))
+
+    def worker(i):
+        bi, bo = bufs[i]
+        for _ in range(per_thr):
+            proc.reduce(8, bi, reduce_mode=K.ReduceMode.Dither, out=bo)
+
+    for rnd in range(2):  # first round warms the per-thread workspaces up
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(n_thr)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        t_par = time.perf_counter() - t0
     entry = {"images_per_s": 1.0 / (t_reduce + t_pal), "reduce_dither_us": t_reduce * 1e6, "palette_us": t_pal * 1e6,
+             "reduce_dither_14_threads_images_per_s": n_thr * per_thr / t_par,
              "h2d_bytes": int(tokyo.nbytes) * 2, "d2h_bytes": int(tokyo.nbytes) + 8 * 16,
              "launches_per_reduce": 2, "what": "ImageProcessor.reduce(8, dither) + .palette(8), pinned host buffers"}
     if rank == 0 and world == 1:
