@@ -312,6 +312,24 @@ def run_ours(args):
                 traffic = json.loads(tp.read_text()).get("lloyd_k8_8192_bytes_per_launch")
             except Exception:
                 traffic = None
+        # FP32 side of the roofline (BASELINE.md sections 2-3): the reference formula costs 12 + 20 k
+        # single operations per pixel; the peak is measured on this GPU (FFMA issue rate)
+        fma_peak = D.fp32_peak(proc)
+        ops_px = 12 + 20 * K_CLUSTERS
+        warp_inst = None
+        if tp.exists():
+            try:
+                warp_inst = json.loads(tp.read_text()).get("lloyd_k8_8192_warp_instructions_per_launch")
+            except Exception:
+                warp_inst = None
+        fp32_roof = {"bound": "fp32", "unit": "Top/s (an FMA counts as one operation)", "ops_per_px_reference_formula": ops_px,
+                     "achieved": n * ops_px / (step_ms * 1e-3) / 1e12, "peak": fma_peak / 1e12,
+                     "frac": n * ops_px / (step_ms * 1e-3) / fma_peak, "peak_source": "measured on this GPU (kmg_dev_fp32_peak)",
+                     "note": "above 1 because the pass evaluates the reference's 20 operations per (pixel, centroid) as 5 FMAs "
+                             "plus a certificate; the binding resource is instruction issue under register-bank limits "
+                             "(DESIGN.md 4.6)",
+                     "issue_frac": (warp_inst * 32 / (step_ms * 1e-3) / fma_peak) if warp_inst else None,
+                     "issue_frac_what": "executed warp instructions of one launch (ncu, profiles/traffic.json) x 32 lanes / time / peak"}
         if world == 1:
             cpu_mpix, cpu_threads, cpu_sec = cpu_iteration_sample(2048, 3)
             cpu_baseline = {"value": cpu_mpix, "unit": "Mpix/s", "cores": cpu_threads, "kind": "port",
@@ -332,6 +350,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd<KT=8,KCAP=8,256 threads,4 px/thread,thread-private atomic slots,2 blocks/SM,table in the constant bank>",
                          "kernel_ms": step_ms},
+            "roofline_fp32": fp32_roof,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": K_CLUSTERS * 16 + 64,
                     "call": f"kmg_kmeans_palette(max_dim=0, {E2E_PASSES} passes) on a pinned host image", "steps": e2e_steps},

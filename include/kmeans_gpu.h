@@ -216,6 +216,9 @@ int kmg_dev_srgb_table(kmg_ctx* ctx, float table_out[256]);
 /* Largest |approximate Lab - exact Lab| (Euclidean) over all 2^24 sRGB colours, as used by the
  * remap kernels' near-tie certificate — exposed for the parity test of that bound. */
 int kmg_dev_fast_lab_error(kmg_ctx* ctx, float* max_err_out);
+/* Measured FP32 (non-tensor) peak of the device in fused multiply-adds per second (x 2 = FLOP/s):
+ * the FP32 side of the roofline bench.py reports next to the HBM side. */
+int kmg_dev_fp32_peak(kmg_ctx* ctx, double* fma_per_second_out);
 /* Number of kernels this library launched on behalf of ctx since creation. */
 uint64_t kmg_launch_count(kmg_ctx* ctx);
 

@@ -1198,6 +1198,35 @@ extern "C" int kmg_dev_srgb_table(kmg_ctx* ctx, float* table_out) {
   return KMG_OK;
 }
 
+extern "C" int kmg_dev_fp32_peak(kmg_ctx* ctx, double* fma_per_second_out) {
+  if (!ctx || !fma_per_second_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_fp32_peak: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  float* d = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CU(cudaMalloc((void**)&d, 4));
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 4096, grid = ctx->sms * 8;
+  float best_ms = 1e30f;
+  cudaError_t e = cudaSuccess;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {  // the first launch warms the clocks up
+    cudaEventRecord(e0, ctx->stream);
+    k_fp32_peak<<<grid, 256, 0, ctx->stream>>>(d, iters);
+    LAUNCHED(ctx);
+    cudaEventRecord(e1, ctx->stream);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(KMG_ERR_CUDA, "kmg_dev_fp32_peak: %s", cudaGetErrorString(e));
+  *fma_per_second_out = (double)grid * 256.0 * iters * 64.0 / ((double)best_ms * 1e-3);
+  return KMG_OK;
+}
+
 extern "C" int kmg_dev_fast_lab_error(kmg_ctx* ctx, float* max_err_out) {
   if (!ctx || !max_err_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_fast_lab_error: NULL argument");
   CU(cudaSetDevice(ctx->device));

@@ -1501,6 +1501,27 @@ __global__ void __launch_bounds__(256) k_synth(uint32_t* __restrict__ rgba, unsi
 }
 
 // Max |fast Lab - exact Lab| over all 2^24 colours (test hook for the LAB_ERR bound).
+// FP32 (non-tensor) issue peak of the device, for the FP32 side of the roofline: 16 independent
+// FFMA chains per thread with a constant-bank multiplier (the form that issues every cycle: two
+// register reads in different banks), 8 resident blocks per SM.
+__constant__ float c_peak_mul[4] = {1.0000001f, 0.9999999f, 1.0000002f, 0.9999998f};
+__global__ void __launch_bounds__(256) k_fp32_peak(float* __restrict__ out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0f + (float)(threadIdx.x + i) * 1e-6f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], c_peak_mul[r], 1e-7f);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) k_fast_lab_error(const float* __restrict__ lut_g, float* __restrict__ out_max) {
   __shared__ float lut[256];
   lut[threadIdx.x] = lut_g[threadIdx.x];

@@ -86,6 +86,13 @@ def fast_lab_error(proc: ImageProcessor) -> float:
     return float(v.value)
 
 
+def fp32_peak(proc: ImageProcessor) -> float:
+    """Measured non-tensor FP32 peak of the device, fused multiply-adds per second."""
+    v = C.c_double(0)
+    _native.check(proc._lib.kmg_dev_fp32_peak(proc.ctx, C.byref(v)))
+    return float(v.value)
+
+
 class Job:
     """A k-means problem resident on the device (kmg_job)."""
 
