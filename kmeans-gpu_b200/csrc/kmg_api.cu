@@ -70,7 +70,6 @@ static int lloyd_variant_index(int kcap, int v) {
   return -1;
 }
 #define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
-#define LLOYDGC k_lloyd<0, 0, 256, 4, false, 2, true>  // chunk loop fed from the constant bank (k <= CTAB_BIG_K)
 #define LLOYDGS k_lloyd<0, 0, 256, 4, false, 2, false, true>  // block accumulators in shared memory
 static constexpr uint32_t LLOYDGS_MAX_K = 2048;  // table 52 KiB + accumulators 56 KiB per block
 // Whole-k-means-in-one-launch variants (kmg_small.cuh): <table/accumulator capacity, threads>
@@ -228,16 +227,14 @@ struct kmg_ctx {
   uint32_t xchg_seq = 0x1234567u;          // flag sequence base handed to the next sharded job
   // constant-bank table slots (kmg_kernels.cuh: c_tab), handed to jobs with k <= 8
   void* c_tab_dev = nullptr;
-  void* c_tab_big_dev = nullptr;
-  bool big_const = false;      // KMG_LLOYDG_CONST=1: chunk loop of the k > 32 pass fed from the constant bank (slower)
   bool big_block_acc = true;   // KMG_LLOYDG_BLOCKACC=0: accumulate through L2 atomics instead of shared memory
   int block_flush_log2 = 19;   // KMG_BLOCKACC_FLUSH_LOG2 (10..19): drain interval of the block accumulators (tests)
 };
 
-// Ownership of one slot of the constant-bank tables (c_tab / c_tab_big).  Copies of a job (the
+// Ownership of one slot of the constant-bank tables (c_tab).  Copies of a job (the
 // per-chunk copies of a batched remap) do not own the slot: the copy constructor leaves it empty.
 struct CSlot {
-  int slot = -1, big = 0, device = 0;
+  int slot = -1, device = 0;
   CSlot() = default;
   CSlot(const CSlot&) {}
   CSlot& operator=(const CSlot&) { return *this; }
@@ -271,22 +268,21 @@ struct kmg_job {
 // The constant bank belongs to the device (one copy of the module per device), not to a context:
 // the free list is per device and process-wide.
 static std::mutex g_cslot_mu;
-static std::vector<int> g_cslots_free[2][64];  // [small | big tables][device]
-static bool g_cslots_ready[2][64];
-static int cslot_acquire(kmg_job* j, bool big = false) {
+static std::vector<int> g_cslots_free[64];  // per device
+static bool g_cslots_ready[64];
+static int cslot_acquire(kmg_job* j) {
   kmg_ctx* ctx = j->ctx;
   if (!ctx->c_tab_dev || ctx->device >= 64) return -1;
   std::lock_guard<std::mutex> g(g_cslot_mu);
-  std::vector<int>& fl = g_cslots_free[big][ctx->device];
-  if (!g_cslots_ready[big][ctx->device]) {
-    g_cslots_ready[big][ctx->device] = true;
-    for (int i = (big ? CTAB_BIG_SLOTS : CTAB_SLOTS) - 1; i >= 0; --i) fl.push_back(i);
+  std::vector<int>& fl = g_cslots_free[ctx->device];
+  if (!g_cslots_ready[ctx->device]) {
+    g_cslots_ready[ctx->device] = true;
+    for (int i = CTAB_SLOTS - 1; i >= 0; --i) fl.push_back(i);
   }
   if (fl.empty()) return -1;
   int s = fl.back();
   fl.pop_back();
   j->cs_owner.slot = s;
-  j->cs_owner.big = big ? 1 : 0;
   j->cs_owner.device = ctx->device;
   return s;
 }
@@ -295,7 +291,7 @@ static int cslot_acquire(kmg_job* j, bool big = false) {
 CSlot::~CSlot() {
   if (slot >= 0) {
     std::lock_guard<std::mutex> g(g_cslot_mu);
-    g_cslots_free[big][device].push_back(slot);
+    g_cslots_free[device].push_back(slot);
   }
 }
 
@@ -572,12 +568,9 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
   small_probe(ctx, prop);
   CU(cudaGetSymbolAddress(&ctx->c_tab_dev, c_tab));
-  CU(cudaGetSymbolAddress(&ctx->c_tab_big_dev, c_tab_big));
-  if (const char* e = getenv("KMG_LLOYDG_CONST")) ctx->big_const = atoi(e) != 0;
   if (const char* e = getenv("KMG_LLOYDG_BLOCKACC")) ctx->big_block_acc = atoi(e) != 0;
   if (const char* e = getenv("KMG_BLOCKACC_FLUSH_LOG2")) ctx->block_flush_log2 = std::min(19, std::max(10, atoi(e)));
   CU(cudaFuncSetAttribute(LLOYDGS, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CU(cudaFuncSetAttribute(LLOYDGC, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   for (int v = 0; v < N_LLOYD_VARIANTS; ++v) {
     const LloydVariant& V = LLOYD_VARIANTS[v];
     CU(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.smem));
@@ -726,18 +719,10 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k));
     int grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
-    if (j->k <= (uint32_t)CTAB_BIG_K && ctx->big_const && !ctx->big_block_acc && j->cslot < 0 && !j->cslot_tried) {
-      j->cslot_tried = true;
-      j->cslot = cslot_acquire(j, true);
-    }
     if (j->k <= LLOYDGS_MAX_K && ctx->big_block_acc) {
       smem += (size_t)7 * pad32(j->k) * 4;
       grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
       LLOYDGS<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, ctx->block_flush_log2, j->k);
-    } else if (j->cslot >= 0) {
-      CU(cudaMemcpyAsync((char*)ctx->c_tab_big_dev + (size_t)j->cslot * CTAB_BIG_K * 24, j->P.tab,
-                         (size_t)pad32(j->k) * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
-      LLOYDGC<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, j->cslot, j->k);
     } else {
       LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0, j->k);
     }

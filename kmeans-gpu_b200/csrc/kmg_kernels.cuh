@@ -111,12 +111,8 @@ __device__ __forceinline__ void tab_to_smem(CentRec* s_tab, const CentRec* __res
 constexpr int CTAB_SLOTS = 64;
 constexpr int CTAB_FLOATS = 16 * 6;
 __constant__ float c_tab[CTAB_SLOTS][CTAB_FLOATS];
-// ... and of a table of up to 256 centroids (chunked search): the main loop over chunks reads its
-// 48 scalars per chunk with twelve uniform 128-bit constant loads instead of twelve LDS.128 into
-// vector registers, and its FFMA2 no longer pay the third register-bank read of a vector scalar.
-constexpr int CTAB_BIG_SLOTS = 6;
-constexpr int CTAB_BIG_K = 256;
-__constant__ float c_tab_big[CTAB_BIG_SLOTS][CTAB_BIG_K * 6];
+// (Feeding the chunk loop of the k > 32 search from the constant bank the same way was measured
+// slower — 48 uniform registers per chunk leave no room to prefetch the next chunk — and removed.)
 
 // ------------------------------------------------------------------------------------------------
 // Small utilities
@@ -416,11 +412,10 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
 // and second-best chunk minima.  The precise certificate then runs on the winning chunk alone, so
 // the half-rate ALU pipe sees ~1.1 min/select operations per (pixel, centroid) instead of 5 and
 // the loop is bound by the 5 FMAs of the score.
-template <int P, bool CONV, bool CT = false>
+template <int P, bool CONV>
 __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
                                                float lmax, float cmax, float conv_k, float (&eps)[P],
-                                               unsigned int (&idx)[P], bool (&certified)[P],
-                                               const float* __restrict__ ctab = nullptr) {
+                                               unsigned int (&idx)[P], bool (&certified)[P]) {
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::PixCoef pc[P];
@@ -437,18 +432,10 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
     m2c[i] = 3.0e38f;
     ic[i] = 0;
   }
-  const float* ct = ctab;  // CT: the same table, dense, in the constant bank (uniform-register operands)
-#pragma unroll 1
   for (unsigned int c = 0; c < kp; c += 8) {
     fast::f32x2 s2[8][H];
     float f[48];
-    if (CT) {
-#pragma unroll
-      for (int u = 0; u < 48; ++u) f[u] = ct[u];
-      ct += 48;
-    } else {
-      load_chunk(rec_at(tab, c), f);
-    }
+    load_chunk(rec_at(tab, c), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -982,8 +969,7 @@ __device__ __forceinline__ void lloyd_load(const float4* __restrict__ work, unsi
 // compiler has to assume they do); cstride = distance between components in ints.
 template <int KT, int THREADS, int P, bool PRIVATE, bool CHECK, bool CT = false, bool ATOM = false>
 __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, const CentRec* __restrict__ x_tab,
-                                           const float* __restrict__ ctab_big, unsigned int kp,
-                                           int4* __restrict__ s_acc, unsigned int cstride,
+                                           unsigned int kp, int4* __restrict__ s_acc, unsigned int cstride,
                                            unsigned long long* __restrict__ g_acc, const float4 (&v)[P],
                                            unsigned long long base, unsigned long long n, unsigned int k,
                                            float lmax, float cmax, unsigned int tid, unsigned int& slow) {
@@ -1003,7 +989,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
   if (KT > 0)
     argmin_small<P, (KT > 0 ? KT : 8), false, CT>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
   else
-    argmin_chunked<P, false, CT>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified, ctab_big);
+    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
   // one vote per tile: the exact path is rare (1e-4 .. 1e-2 of the pixels)
   bool need[P], any_need = false;
 #pragma unroll
@@ -1070,7 +1056,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
                                                          unsigned long long n, int color_space,
                                                          int distributed_mode, PeerXchg X, int cslot,
                                                          unsigned int k_arg) {
-  static_assert(!CT || KT == 0 || (KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k");
+  static_assert(!CT || (KT > 0 && KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(16) unsigned char s_tab_static[(KT > 0 && !CT) ? (KT / 8) * CHUNK_BYTES : 16];
   __shared__ bool s_last;
@@ -1080,13 +1066,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
   const unsigned int k = k_arg;  // == st->k; a kernel parameter is provably warp-uniform (loop counters over
                                  // the table then live in uniform registers and can index the constant bank)
   const unsigned int kp = KT > 0 ? (unsigned int)KT : pad32(k);
-  // KT > 0 && CT: no shared-memory table at all; KT == 0 && CT: the shared-memory table serves the
-  // winning-chunk rescan and the exact path, the chunk loop reads the constant bank
+  // CT: no shared-memory table at all
   constexpr bool CT_SMALL = CT && KT > 0;
   const CentRec* s_tab = CT_SMALL ? reinterpret_cast<const CentRec*>(c_tab[cslot])
                                   : reinterpret_cast<const CentRec*>(KT > 0 ? s_tab_static : smem_raw);
   const CentRec* x_tab = CT_SMALL ? J.tab : s_tab;
-  const float* ctab_big = (CT && KT == 0) ? c_tab_big[cslot] : nullptr;
   // PRIVATE: [KCAP][THREADS] slots after the (compile-time sized) table; !PRIVATE && ATOM: block
   // accumulators [7][kp] ints after the runtime-sized table
   constexpr bool BLOCK_ACC = !PRIVATE && ATOM;
@@ -1172,7 +1156,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     for (; tile < full_tiles; tile += gridDim.x) {
       const unsigned long long next = tile + gridDim.x;
       if (next < full_tiles) lloyd_load<THREADS, P, false>(work, next * TILE + tid, n, nxt);
-      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT, ATOM>(s_tab, x_tab, ctab_big, kp, s_acc, CSTRIDE, g_acc, cur,
+      lloyd_tile<KT, THREADS, P, PRIVATE, false, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, cur,
                                                            tile * TILE + tid, n, k, lmax, cmax, tid, slow);
       since_flush += P;
       // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
@@ -1188,7 +1172,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
     if (PRIVATE && since_flush + P > 240) flush();
     float4 tail[P];
     lloyd_load<THREADS, P, true>(work, full_tiles * TILE + tid, n, tail);
-    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT, ATOM>(s_tab, x_tab, ctab_big, kp, s_acc, CSTRIDE, g_acc, tail,
+    lloyd_tile<KT, THREADS, P, PRIVATE, true, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, tail,
                                                         full_tiles * TILE + tid, n, k, lmax, cmax, tid, slow);
   }
   flush();

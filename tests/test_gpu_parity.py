@@ -230,6 +230,50 @@ def test_block_accumulators_drain_mid_pass(K, D, oracle, torch, monkeypatch):
         p.close()
 
 
+@pytest.mark.parametrize("k,env,n_variants", [(7, "KMG_LLOYD8_VARIANT", 6), (13, "KMG_LLOYD16_VARIANT", 4),
+                                              (27, "KMG_LLOYD32_VARIANT", 2)])
+def test_every_lloyd_variant_gives_the_same_sums(K, D, oracle, torch, monkeypatch, k, env, n_variants):
+    """LLOYD_VARIANTS (kmg_api.cu): shared-memory or constant-bank table, atomic or read-modify-write
+    slots, different geometries — every one must produce the oracle's integer sums."""
+    w, h = 700, 500
+    img = oracle.synth(w * h, seed=k, blobs=2 * k).reshape(h, w, 4)
+    lab = oracle.convert(img)
+    cent = lab[np.random.default_rng(k).choice(w * h, k, replace=False)].copy()
+    cent[:, 3] = 1.0
+    want = oracle.partial_sums(lab, oracle.assign(lab, cent), k)
+    for v in range(n_variants):
+        monkeypatch.setenv(env, str(v))
+        p = K.ImageProcessor(0)
+        try:
+            work = D.convert(p, dev_rgba(torch, img))
+            job = D.Job(p, work, w, h, k)
+            job.set_centroids(cent)
+            job.step(1)
+            assert np.array_equal(job.sums(), want), (env, v)
+            job.close()
+        finally:
+            p.close()
+
+
+def test_more_live_jobs_than_constant_bank_slots(proc, D, K, oracle, torch):
+    """64 slots of the constant bank per device: job 65 and later fall back to the shared-memory
+    table; all 80 jobs alive at once must agree with the oracle."""
+    w, h, k = 320, 240, 6
+    img = oracle.synth(w * h, seed=3, blobs=12).reshape(h, w, 4)
+    lab = oracle.convert(img)
+    cent = lab[np.random.default_rng(3).choice(w * h, k, replace=False)].copy()
+    cent[:, 3] = 1.0
+    want = oracle.partial_sums(lab, oracle.assign(lab, cent), k)
+    work = D.convert(proc, dev_rgba(torch, img))
+    jobs = [D.Job(proc, work, w, h, k) for _ in range(80)]
+    for j in jobs:
+        j.set_centroids(cent)
+        j.step(1)
+    for j in jobs:
+        assert np.array_equal(j.sums(), want)
+        j.close()
+
+
 def test_lloyd_empty_cluster_keeps_centroid(proc, D, K, oracle, torch):
     """choose_centroid.wgsl:185-194: an empty cluster keeps its centroid and never counts as
     converged, so the loop runs to the 128-iteration cap (core/src/modules.rs:764-766)."""
