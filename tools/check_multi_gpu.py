@@ -70,6 +70,36 @@ for (W, H, k, passes) in ((1024, 96 * world, 8, 12), (640, 50 * world, 16, 9), (
     if not torch.equal(t, ref):
         print(f"rank {rank}: centroids differ from rank 0")
         failures += 1
+# fewer distinct colours than clusters: the late init rounds see an all-zero maximum, which resolves
+# to global pixel 0 — held by rank 0 alone, every other rank posts "no candidate"
+W, H, k = 64, 16 * world, 6
+host = np.zeros((H, W, 4), np.uint8)
+host[..., 3] = 255
+host[:, :20, 0] = 200
+host[:, 20:40, 1] = 180
+host[H // 2:, 40:, 2] = 90
+rows = K.row_shards(H, world)[rank]
+opts = K.Opts(max_dim=0, max_iter=3, check_every=0)
+work = D.convert(proc, torch.from_numpy(host[rows[0]:rows[1]].copy()).to(dev))
+job = D.Job(proc, work, W, rows[1] - rows[0], k, opts=opts)
+job.set_shard(W, H, rows[0])
+idx, dst = job.init()
+job.run()
+cent = job.centroids()
+job.close()
+if rank == 0:
+    solo = K.ImageProcessor(local)
+    work1 = D.convert(solo, torch.from_numpy(host).to(dev))
+    job1 = D.Job(solo, work1, W, H, k, opts=opts)
+    idx1, dst1 = job1.init()
+    job1.run()
+    cent1 = job1.centroids()
+    job1.close()
+    solo.close()
+    ok = idx.tolist() == idx1.tolist() and np.array_equal(dst.view(np.uint32), dst1.view(np.uint32)) and \
+        np.array_equal(cent.view(np.uint32), cent1.view(np.uint32))
+    print(f"{W}x{H} four colours k={k}: picks {idx.tolist()} vs single {idx1.tolist()}: {'OK' if ok else 'MISMATCH'}")
+    failures += 0 if ok else 1
 flag = torch.tensor([failures], device=dev)
 dist.all_reduce(flag)
 D.comm_destroy(proc)
