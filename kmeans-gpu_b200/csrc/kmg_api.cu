@@ -5,6 +5,7 @@
 // (core/shaders/*.wgsl) is a kernel launch here.  The only host arithmetic is what the reference
 // also does on the host (the `palette` crate conversions, kmg_host.cpp).
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -180,14 +181,23 @@ struct Buf {
 struct Workspace {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // created on first use: uploads that overlap kernels on `stream`
+  cudaStream_t out_stream = nullptr;   // ... and read-backs that do (pipelined reduce)
   std::vector<cudaEvent_t> band_done;  // one per band in flight (banded upload + convert)
+  std::vector<cudaEvent_t> band_out;   // remap of a band finished (pipelined reduce)
+  cudaEvent_t palette_ready = nullptr;
   Buf in, out, small, work, dmin, blob;
   JobState* h_state = nullptr;  // pinned
   void release() {
     for (cudaEvent_t e : band_done) cudaEventDestroy(e);
     band_done.clear();
+    for (cudaEvent_t e : band_out) cudaEventDestroy(e);
+    band_out.clear();
+    if (palette_ready) cudaEventDestroy(palette_ready);
+    palette_ready = nullptr;
     if (copy_stream) cudaStreamDestroy(copy_stream);
     copy_stream = nullptr;
+    if (out_stream) cudaStreamDestroy(out_stream);
+    out_stream = nullptr;
     in.release();
     out.release();
     small.release();
@@ -1465,6 +1475,83 @@ extern "C" int kmg_remap(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t
   return KMG_OK;
 }
 
+// reduce() of a large host image that is shrunk before clustering (the reference's default,
+// core/src/structures.rs:67-74), as one pipeline.  The k-means only reads the source rows the
+// bilinear taps touch (resize.wgsl:5-19: at most 2 per clustered row, a few per cent of a large
+// image), so those rows are uploaded first and clustered; only then does the whole image stream
+// through: upload of band i+1 (copy stream), remap of band i (main stream) and read-back of band
+// i-1 (output stream) overlap, and the call costs about one direction of PCIe traffic instead of
+// upload + kernels + read-back in series.  The full upload starts after the k-means so that no
+// copy ever writes rows a running kernel reads.
+static int reduce_pipelined(kmg_ctx* ctx, Workspace* ws, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t k, int cs,
+                            int mode, const kmg_opts& o, const std::vector<uint8_t>& tap_rows, uint8_t* out_rgba,
+                            float* centroids_out, uint32_t* passes_out) {
+  cudaStream_t s = ws->stream;
+  const size_t row_bytes = (size_t)w * 4, bytes = row_bytes * h;
+  TRY(ws->in.ensure(bytes));
+  TRY(ws->out.ensure(bytes));
+  if (!ws->copy_stream) CU(cudaStreamCreateWithFlags(&ws->copy_stream, cudaStreamNonBlocking));
+  if (!ws->out_stream) CU(cudaStreamCreateWithFlags(&ws->out_stream, cudaStreamNonBlocking));
+  if (!ws->palette_ready) CU(cudaEventCreateWithFlags(&ws->palette_ready, cudaEventDisableTiming));
+  // 1. the rows the shrink reads, as runs of consecutive rows
+  for (uint32_t r = 0; r < h;) {
+    if (!tap_rows[r]) {
+      ++r;
+      continue;
+    }
+    uint32_t e = r;
+    while (e < h && tap_rows[e]) ++e;
+    CU(cudaMemcpyAsync((uint8_t*)ws->in.p + row_bytes * r, rgba + row_bytes * r, row_bytes * (e - r), cudaMemcpyHostToDevice, s));
+    r = e;
+  }
+  // 2. k-means on the shrunk image (table, palette and dither threshold end up in the job blob)
+  kmg_job job;
+  bool prepared = false;
+  TRY(kmeans_on_device(ctx, ws, (const uint8_t*)ws->in.p, w, h, k, cs, o, &job, &prepared, tail_for_mode(mode)));
+  if (!prepared) TRY(launch_prepare(&job, true, s));
+  CU(cudaEventRecord(ws->palette_ready, s));
+  CU(cudaStreamWaitEvent(ws->copy_stream, ws->palette_ready, 0));
+  // 3. the image, band by band
+  const uint32_t band_rows = (uint32_t)std::max<size_t>(4, (((size_t)16 << 20) / row_bytes) & ~(size_t)3);
+  const uint32_t n_bands = (h + band_rows - 1) / band_rows;
+  while (ws->band_done.size() < n_bands || ws->band_out.size() < n_bands) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    (ws->band_done.size() < n_bands ? ws->band_done : ws->band_out).push_back(e);
+  }
+  for (uint32_t b = 0; b < n_bands; ++b) {
+    const uint32_t r0 = b * band_rows, rows = std::min(band_rows, h - r0);
+    const size_t off = row_bytes * r0, sz = row_bytes * rows;
+    CU(cudaMemcpyAsync((uint8_t*)ws->in.p + off, rgba + off, sz, cudaMemcpyHostToDevice, ws->copy_stream));
+    CU(cudaEventRecord(ws->band_done[b], ws->copy_stream));
+    CU(cudaStreamWaitEvent(s, ws->band_done[b], 0));
+    TRY(launch_remap(&job, (const uint8_t*)ws->in.p + off, w, rows, mode, (uint8_t*)ws->out.p + off, s, true));
+    CU(cudaEventRecord(ws->band_out[b], s));
+    CU(cudaStreamWaitEvent(ws->out_stream, ws->band_out[b], 0));
+    CU(cudaMemcpyAsync(out_rgba + off, (const uint8_t*)ws->out.p + off, sz, cudaMemcpyDeviceToHost, ws->out_stream));
+  }
+  if (centroids_out) CU(cudaMemcpyAsync(centroids_out, job.P.cent, (size_t)k * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaStreamSynchronize(ws->out_stream));
+  CU(cudaStreamSynchronize(ws->copy_stream));
+  if (passes_out) *passes_out = ws->h_state->passes;
+  return KMG_OK;
+}
+
+// Source rows the bilinear shrink of a w x h image to iw x ih reads (resize_taps in
+// kmg_kernels.cuh, same f32 arithmetic), with one row of margin on either side.
+static size_t shrink_tap_rows(uint32_t h, uint32_t ih, std::vector<uint8_t>* rows) {
+  rows->assign(h, 0);
+  for (uint32_t gy = 0; gy < ih; ++gy) {
+    const float py = ((float)gy / (float)ih) * (float)h - 0.5f;
+    const long long y0 = (long long)std::floor(py);
+    for (long long r = y0 - 1; r <= y0 + 2; ++r) (*rows)[(size_t)std::min<long long>(std::max<long long>(r, 0), (long long)h - 1)] = 1;
+  }
+  size_t count = 0;
+  for (uint8_t v : *rows) count += v;
+  return count;
+}
+
 extern "C" int kmg_reduce(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t k, int cs, int mode,
                           const kmg_opts* opts, uint8_t* out_rgba, float* centroids_out, uint32_t* passes_out) {
   TRY(check_image_args("kmg_reduce", ctx, rgba, w, h, k, cs));
@@ -1476,6 +1563,17 @@ extern "C" int kmg_reduce(kmg_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_
   WsGuard guard{ctx, ws};
   cudaStream_t s = ws->stream;
   const size_t bytes = (size_t)w * h * 4;
+  {
+    const kmg_opts po = resolve_opts(opts);
+    if (po.max_dim != 0 && (w > po.max_dim || h > po.max_dim) && bytes >= ((size_t)32 << 20) &&
+        !getenv("KMG_NO_REDUCE_PIPELINE")) {  // the switch exists for A/B timing
+      uint32_t iw, ih;
+      kmg_resized_dims(w, h, po.max_dim, &iw, &ih);
+      std::vector<uint8_t> tap_rows;
+      if (shrink_tap_rows(h, ih, &tap_rows) * 2 <= h)  // worth it when the taps (plus margin) touch at most half of the rows
+        return reduce_pipelined(ctx, ws, rgba, w, h, k, cs, mode, po, tap_rows, out_rgba, centroids_out, passes_out);
+    }
+  }
   TRY(ws->out.ensure(bytes));
   const kmg_opts o = resolve_opts(opts);
   bool plane_ready = false;

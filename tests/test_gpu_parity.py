@@ -606,6 +606,28 @@ def test_banded_upload_of_a_large_unshrunk_image(proc, K, oracle):
     assert np.array_equal(out.rgba, oracle.remap_replace(img, ocent))
 
 
+def test_reduce_of_a_large_host_image_is_pipelined(proc, K, oracle):
+    """kmg_reduce on a host image >= 32 MiB that is shrunk before clustering: the rows the bilinear
+    taps read are uploaded first and clustered, then the image streams through upload / remap /
+    read-back bands.  Same bytes as the oracle's reduce; ragged geometry; pageable and pinned."""
+    w, h = 3001, 2803  # 33.6 MB, bands of 1396 rows + a short one; shrinks to 256 x 239
+    img = oracle.synth(w * h, seed=31, blobs=10).reshape(h, w, 4)
+    n0 = proc.launch_count()
+    out, cent, passes = proc.reduce(5, img, reduce_mode=K.ReduceMode.Dither, return_details=True)
+    assert proc.launch_count() - n0 == 1 + 3  # one-launch k-means + one remap launch per band
+    want, ocent, opasses = oracle.reduce(img, 5, "dither")
+    assert passes == opasses and np.array_equal(bits(cent), bits(ocent))
+    assert np.array_equal(out.rgba, want)
+    pin_in, pin_out = K.pinned_empty((h, w, 4)), K.pinned_empty((h, w, 4))
+    pin_in[...] = img
+    proc.reduce(5, pin_in, reduce_mode=K.ReduceMode.Replace, out=pin_out)
+    assert np.array_equal(pin_out, oracle.reduce(img, 5, "replace")[0])
+    # portrait image (the shrink rule takes the other branch), staged k-means (no fused kernel)
+    imgp = np.ascontiguousarray(img.transpose(1, 0, 2))
+    outp = proc.reduce(5, imgp, reduce_mode=K.ReduceMode.Dither, opts=K.Opts(fused_kmeans=False))
+    assert np.array_equal(outp.rgba, oracle.reduce(imgp, 5, "dither")[0])
+
+
 def test_concurrent_staged_jobs_share_the_constant_bank(proc, K, oracle, tokyo):
     """Staged launches (no shrink, > 65,536 clustered pixels) with k <= 16 keep their table in a
     per-job slot of the constant bank: jobs running at the same time on different streams must not
