@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <set>
 #include <vector>
 
 #include "../../include/kmeans_gpu.h"
@@ -179,23 +180,21 @@ extern "C" int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32
     nodes[at].b += c[2];
     nodes[at].count += 1;
   }
-  // Like the reference: a sequence kept in descending order whose back (the smallest node) is
-  // popped.  Node keys only change while the node is outside the sequence, so it is always sorted
-  // and the binary searches are exact.
+  // The reference keeps a deque sorted in descending order, pops its back (the smallest node) and
+  // finds / re-inserts parents by binary search — O(n) per step.  Node keys only change while the
+  // node is outside the sequence, so an ordered set with the same strict total order is equivalent
+  // and O(log n) per step.
   OctLess less{&nodes};
-  auto greater = [&](size_t a, size_t b) { return less(b, a); };
-  std::vector<size_t> leaves;
+  std::set<size_t, OctLess> leaves(less);
   for (size_t i = 0; i < nodes.size(); ++i)
-    if (nodes[i].count > 0) leaves.push_back(i);
-  std::sort(leaves.begin(), leaves.end(), greater);
+    if (nodes[i].count > 0) leaves.insert(i);
   while (leaves.size() > color_count) {
-    const size_t id = leaves.back();
-    leaves.pop_back();
+    const size_t id = *leaves.begin();
+    leaves.erase(leaves.begin());
     OctNode& node = nodes[id];
     if (node.parent < 0) continue;
     const size_t pid = (size_t)node.parent;
-    auto it = std::lower_bound(leaves.begin(), leaves.end(), pid, greater);
-    if (it != leaves.end() && *it == pid) leaves.erase(it);
+    leaves.erase(pid);  // present only if the parent already holds pixels (keyed by its current state)
     OctNode& par = nodes[pid];
     par.r += node.r;
     par.g += node.g;
@@ -204,8 +203,7 @@ extern "C" int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32
     par.child_count -= 1;
     par.children[node.color_index] = -1;
     node.parent = -1;
-    it = std::lower_bound(leaves.begin(), leaves.end(), pid, greater);
-    if (it == leaves.end() || *it != pid) leaves.insert(it, pid);
+    leaves.insert(pid);
   }
   std::vector<uint32_t> pal;
   for (size_t id : leaves) {
