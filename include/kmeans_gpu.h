@@ -136,7 +136,8 @@ void kmg_sort_palette_by_lightness(uint8_t* colors_rgba8, uint32_t count);
  * pixels octree_palette hands it (the image, or its <= 128 px shrink from kmg_resize,
  * core/src/lib.rs:288-316).  colors_out must hold color_count x 4 bytes; *count_out <= color_count
  * colours are written, sorted as (r,g,b,a) tuples and de-duplicated; the caller then sorts them
- * with kmg_sort_palette_by_lightness (lib.rs:318-329). */
+ * with kmg_sort_palette_by_lightness (lib.rs:318-329).  n_pixels < 2^28 (the reference passes at
+ * most 128 x 128).  Host-only: needs no device and no kmg_ctx. */
 int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32_t color_count, uint8_t* colors_out,
                        uint32_t* count_out);
 

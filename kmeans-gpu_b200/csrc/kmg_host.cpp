@@ -128,11 +128,11 @@ extern "C" void kmg_sort_palette_by_lightness(uint8_t* colors, uint32_t count) {
 // node, sorted as (r,g,b,a) tuples and de-duplicated (octree.rs:104-109,128-135).
 namespace {
 
-struct OctNode {
+struct OctNode {  // node ids fit 32 bits: at most 8 new nodes per pixel, < 2^28 pixels accepted
   uint32_t level = 0;
   uint32_t color_index = 0;
-  int64_t parent = -1;
-  int64_t children[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  int32_t parent = -1;
+  int32_t children[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
   uint32_t child_count = 0;
   uint64_t count = 0, r = 0, g = 0, b = 0;
 };
@@ -157,7 +157,9 @@ extern "C" int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32
   if (!count_out || (n_pixels && !rgba) || (color_count && !colors_out)) return KMG_ERR_BAD_ARG;
   *count_out = 0;
   if (color_count == 0) return KMG_OK;  // octree.rs:67-69
+  if (n_pixels >= (1ull << 28)) return KMG_ERR_BAD_ARG;  // the reference hands it at most 128 x 128 pixels
   std::vector<OctNode> nodes(1);
+  nodes.reserve((size_t)std::min<uint64_t>(n_pixels * 8 + 1, 1u << 20));
   for (uint64_t p = 0; p < n_pixels; ++p) {
     const uint8_t* c = rgba + 4 * p;
     size_t at = 0;
@@ -168,8 +170,8 @@ extern "C" int kmg_octree_palette(const uint8_t* rgba, uint64_t n_pixels, uint32
         OctNode child;
         child.level = level;
         child.color_index = ci;
-        child.parent = (int64_t)at;
-        nodes[at].children[ci] = (int64_t)nodes.size();
+        child.parent = (int32_t)at;
+        nodes[at].children[ci] = (int32_t)nodes.size();
         nodes[at].child_count += 1;
         nodes.push_back(child);
       }
