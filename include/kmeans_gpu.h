@@ -179,7 +179,7 @@ int kmg_job_run(kmg_job* job, uint32_t* passes_out, void* stream);
 int kmg_job_stats(kmg_job* job, uint32_t* converged_out, uint32_t* passes_out, uint64_t* slow_pixels_out,
                   void* stream);
 
-/* Reduced integer sums of the last pass: k x {sum0, sum1, sum2, count}, sums in units of 2^-16
+/* Reduced integer sums of the last pass: k x {sum0, sum1, sum2, count}, sums in units of 2^-15
  * (the k x 4 accumulators the multi-GPU path all-reduces; sums of shards add up exactly). */
 int kmg_job_get_sums(kmg_job* job, int64_t* sums_out, void* stream);
 

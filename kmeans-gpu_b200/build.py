@@ -19,7 +19,9 @@ def needs_build() -> bool:
 
 def build(force: bool = False) -> Path:
     if force or needs_build():
-        subprocess.check_call(["make", "-C", str(CSRC)] + (["-B"] if force else []))
+        # -B always: needs_build() has already decided that the library is stale, whatever make's
+        # own dependency list thinks
+        subprocess.check_call(["make", "-C", str(CSRC), "-B"])
     return LIB
 
 

@@ -20,6 +20,7 @@
 #include "../../include/kmeans_gpu.h"
 #include "kmg_kernels.cuh"
 #include "kmg_small.cuh"
+#include "kmg_lloyd_ring.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -46,14 +47,21 @@ struct LloydVariant {
 static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
 #define LV8(P, MINB, CT, ATOM, T) k_lloyd<8, 8, T, P, true, MINB, CT, ATOM>, 8, T, P, CT, (size_t)8 * T * 16
 #define LV16(P, MINB, CT, ATOM) k_lloyd<16, 16, 256, P, true, MINB, CT, ATOM>, 16, 256, P, CT, (size_t)16 * 256 * 16
+// warp-specialised TMA ring (kmg_lloyd_ring.cuh): 8 consumer warps + 1 producer warp, P px per lane and stage, D stages
+#define LVR(P, D, MINB) k_lloyd_ring<8, 8, P, D, MINB>, 8, 288, P, true, (size_t)RingLayout<8, 8, P, D>::BYTES
 static const LloydVariant LLOYD_VARIANTS[] = {
     // k <= 8
+    {LVR(2, 8, 2), "TMA ring 8 x 8 KiB, table resident in uniform registers, 8+1 warps, 2 blocks/SM"},
     {LV8(4, 2, true, true, 256), "const table, atomic slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(4, 2, false, true, 256), "smem table, atomic slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(4, 2, false, false, 256), "smem table, 128-bit RMW slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(4, 3, true, true, 256), "const table, atomic slots, 256 thr x 4 px, 3 blocks/SM"},
     {LV8(4, 2, true, false, 256), "const table, RMW slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(2, 3, false, false, 256), "smem table, RMW slots, 256 thr x 2 px, 3 blocks/SM"},
+    {LVR(2, 4, 2), "TMA ring 4 x 8 KiB, 2 blocks/SM"},
+    {LVR(4, 4, 2), "TMA ring 4 x 16 KiB, 2 blocks/SM"},
+    {LVR(2, 4, 3), "TMA ring 4 x 8 KiB, 3 blocks/SM"},
+    {LVR(8, 2, 2), "TMA ring 2 x 32 KiB, 2 blocks/SM"},
     // k <= 16
     {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
     {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
@@ -544,6 +552,8 @@ static kmg_opts resolve_opts(const kmg_opts* in) {
   return o;
 }
 
+static int ctx_setup(kmg_ctx* ctx, const cudaDeviceProp& prop);
+
 extern "C" int kmg_create(int device, kmg_ctx** out) {
   if (!out) return fail(KMG_ERR_BAD_ARG, "kmg_create: out is NULL");
   *out = nullptr;
@@ -564,6 +574,16 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
   kmg_ctx* ctx = new kmg_ctx();
   ctx->device = device;
   ctx->sms = prop.multiProcessorCount;
+  const int r = ctx_setup(ctx, prop);
+  if (r != KMG_OK) {
+    kmg_destroy(ctx);  // releases whatever ctx_setup had created (stream, table, workspaces)
+    return r;
+  }
+  *out = ctx;
+  return KMG_OK;
+}
+
+static int ctx_setup(kmg_ctx* ctx, const cudaDeviceProp& prop) {
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU(cudaMalloc((void**)&ctx->d_lut, 256 * sizeof(float)));
   k_build_srgb_table<<<1, 256, 0, ctx->stream>>>(ctx->d_lut);
@@ -602,7 +622,6 @@ extern "C" int kmg_create(int device, kmg_ctx** out) {
     }
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  *out = ctx;
   return KMG_OK;
 }
 
@@ -724,7 +743,7 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
     if (V.const_tab)  // the table of this pass goes to the job's slot of the constant bank (see c_tab)
       CU(cudaMemcpyAsync((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4, j->P.tab,
                          (size_t)V.kcap * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
-    int grid = grid_for(ctx, n, V.threads * V.px, ctx->occ_lloyd[v]);
+    int grid = grid_for(ctx, n, (V.threads == 288 ? 256 : V.threads) * V.px, ctx->occ_lloyd[v]);
     V.fn<<<grid, V.threads, V.smem, s>>>(j->P, j->work, n, j->color_space, partial, X, V.const_tab ? j->cslot : 0, j->k);
   } else {
     size_t smem = tab_smem_bytes(pad32(j->k));

@@ -49,7 +49,7 @@ struct JobPtrs {
   JobState* st;
   float4* cent;                // k
   CentRec* tab;                // k padded to a multiple of 32 with MASKED entries
-  long long* acc;              // acc_copies x k x 4  (sum0,sum1,sum2,count), fixed-point 2^-16
+  long long* acc;              // acc_copies x k x 4  (sum0,sum1,sum2,count), fixed-point 2^-15
   long long* last;             // k x 4 — the reduced sums of the last finalised pass
   unsigned long long* keys;    // k  — arg-max keys of the init rounds
   uint32_t* pal;               // k  — centroids reverted to RGBA8
@@ -809,7 +809,7 @@ __global__ void k_init_pick(JobPtrs J, const float4* __restrict__ work, unsigned
 // Lloyd pass = assignment (K5) + centroid update (K6/K7 for every cluster) in ONE sweep over the
 // cached work plane: 16 B/px read, nothing written but k x 4 integer sums.
 //
-// Sums are exact integers, rint(v * 2^16) accumulated in int32 thread-private shared-memory slots
+// Sums are exact integers, rint(v * 2^15) accumulated in int32 thread-private shared-memory slots
 // (PRIVATE: conflict-free 128-bit read-modify-write, flushed before they can overflow) or sent
 // straight to L2 with 64-bit reductions into a per-block copy (large k).  Integer addition
 // commutes, so the result is independent of block scheduling, grid size and of how many GPUs share
@@ -910,9 +910,9 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, int mode, const
       const double cnt = (double)s[3];
       float4 prev = J.cent[c];
       float4 nc;
-      nc.x = (float)(((double)s[0] / cnt) * (1.0 / 65536.0));
-      nc.y = (float)(((double)s[1] / cnt) * (1.0 / 65536.0));
-      nc.z = (float)(((double)s[2] / cnt) * (1.0 / 65536.0));
+      nc.x = (float)(((double)s[0] / cnt) * ex::FIXED_UNIT);
+      nc.y = (float)(((double)s[1] / cnt) * ex::FIXED_UNIT);
+      nc.z = (float)(((double)s[2] / cnt) * ex::FIXED_UNIT);
       nc.w = 1.0f;
       J.cent[c] = nc;
       conv += (ex::cie94(nc.x, nc.y, nc.z, prev.x, prev.y, prev.z) < st->conv_threshold) ? 1u : 0u;
@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
       lloyd_tile<KT, THREADS, P, PRIVATE, false, CT, ATOM>(s_tab, x_tab, kp, s_acc, CSTRIDE, g_acc, cur,
                                                            tile * TILE + tid, n, k, lmax, cmax, tid, slow);
       since_flush += P;
-      // |v| < 2^7 colour units -> |fixed| < 2^23; 240 pixels stay below 2^31.
+      // |v| < 2^7 colour units -> |fixed| < 2^22; 240 pixels stay far below 2^31.
       if (PRIVATE && since_flush + P > 240) flush();
       // block accumulators: 2^19 pixels of the block (since_flush counts pixels per thread)
       if (BLOCK_ACC && (since_flush + P) * THREADS > block_flush_px) flush_block();

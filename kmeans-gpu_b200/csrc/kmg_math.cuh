@@ -171,12 +171,17 @@ __device__ __forceinline__ uint32_t rgbf_to_rgba8(float r, float g, float b, flo
   return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(w) << 24);
 }
 
-// Fixed-point unit of the centroid sums: rint(v * 2^16) (exact product, one rounding).  The
-// product is formed by adding 16 to the exponent field (integer pipe instead of the FMA pipe):
-// identical to v * 65536.0f for every normal |v| < 2^111; zeros and denormals give values far
-// below 0.5, which round to 0 exactly as the true product does.
+// Fixed-point unit of the centroid sums: rint(v * 2^15), ties to even.  For |v| < 128 — every Lab
+// or RGB component of an sRGB8 colour — the IEEE sum v + 384.0f lies in [256, 512), whose ulp is
+// 2^-15: the one rounding of the addition is the rounding wanted, and the integer sits in the low
+// mantissa bits.  One FADD and one integer subtraction, no conversion instruction (F2I runs on the
+// quarter-rate XU pipe); kernels that accumulate many pixels add the raw bits and take
+// count * FIXED_MAGIC_BITS out once (kmg_lloyd_ring.cuh).
+constexpr float FIXED_MAGIC = 384.0f;
+constexpr unsigned int FIXED_MAGIC_BITS = 0x43C00000u;
+constexpr double FIXED_UNIT = 1.0 / 32768.0;
 __device__ __forceinline__ int to_fixed(float v) {
-  return __float2int_rn(__int_as_float(__float_as_int(v) + (16 << 23)));
+  return __float_as_int(__fadd_rn(v, FIXED_MAGIC)) - (int)FIXED_MAGIC_BITS;
 }
 
 }  // namespace ex

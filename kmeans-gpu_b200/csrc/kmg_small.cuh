@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_kmeans_small(SmallParams prm, Jo
       if (s[3] > 0) {  // warp-uniform
         const double cnt = (double)s[3];
         const long long mine = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
-        const float comp = (float)(((double)mine / cnt) * (1.0 / 65536.0));
+        const float comp = (float)(((double)mine / cnt) * ex::FIXED_UNIT);
         float4 nc;
         nc.x = __shfl_sync(0xffffffffu, comp, 0);
         nc.y = __shfl_sync(0xffffffffu, comp, 1);

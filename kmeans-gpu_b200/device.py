@@ -153,7 +153,7 @@ class Job:
         return {"converged": conv.value, "passes": passes.value, "slow_pixels": slow.value}
 
     def sums(self, stream=None) -> np.ndarray:
-        """k x (sum0, sum1, sum2, count) of the last pass, sums in units of 2^-16."""
+        """k x (sum0, sum1, sum2, count) of the last pass, sums in units of 2^-15."""
         acc = np.zeros((self.k, 4), np.int64)
         _native.check(self.proc._lib.kmg_job_get_sums(self._job, acc.ctypes.data_as(C.POINTER(C.c_int64)),
                                                       _stream_ptr(stream)))

@@ -260,16 +260,16 @@ inline uint32_t assign_one(const float* px, const float* cent, uint32_t k, float
   return found;
 }
 
-constexpr double FIXED_SCALE = 65536.0;  // 2^16 fixed-point units per colour unit
+constexpr double FIXED_SCALE = 32768.0;  // 2^15 fixed-point units per colour unit
 
-inline int64_t to_fixed(float v) { return (int64_t)std::nearbyintf(v * 65536.0f); }
+inline int64_t to_fixed(float v) { return (int64_t)std::nearbyintf(v * 32768.0f); }
 
 // core/shaders/choose_centroid.wgsl:73-206 — per-cluster mean + convergence flags (the scan
 // machinery is an implementation detail; its f32 summation order is timing dependent, so two
 // well-defined sums are offered):
 //   sum_mode 0: f64 accumulation of the f32 values, divide, cast to f32;
-//   sum_mode 1: exact integer accumulation of rint(v * 2^16) (order independent, what the CUDA
-//               library does), mean = (double) sum / (double) count * 2^-16, cast to f32.
+//   sum_mode 1: exact integer accumulation of rint(v * 2^15) (order independent, what the CUDA
+//               library does), mean = (double) sum / (double) count * 2^-15, cast to f32.
 // Empty clusters keep their centroid and contribute 0 to the convergence count (:185-194).
 uint32_t update_centroids(const float* work, const uint32_t* labels, size_t n, uint32_t k, float* cent,
                           float threshold, int sum_mode, uint64_t* counts_out) {

@@ -87,7 +87,7 @@ def test_kmeans_intermediate_kats(oracle, tokyo):
 
 
 def test_sum_modes_agree(oracle, tokyo):
-    """Fixed-point (2^-16) sums and f64 sums give the same centroids to well below 1e-4 Lab."""
+    """Fixed-point (2^-15) sums and f64 sums give the same centroids to well below 1e-4 Lab."""
     c0, p0 = oracle.kmeans(tokyo, 8, opts=oracle.default_opts(sum_mode=0))
     c1, p1 = oracle.kmeans(tokyo, 8, opts=oracle.default_opts(sum_mode=1))
     assert p0 == p1
