@@ -134,14 +134,69 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} blobs({BLOBS}) k={K_CLUSTERS} Lab assign+update iteration per GPU", "k": K_CLUSTERS,
-                   "bytes_per_px": BYTES_PER_PX},
+        "config": {"workload": f"{side}x{side} crop (bounded CPU sample) of the {W}x{H} blobs({BLOBS}) k={K_CLUSTERS} Lab image: "
+                               "assign+update iteration, oracle port on the host cores",
+                   "k": K_CLUSTERS, "bytes_per_px": BYTES_PER_PX, "same_config": False,
+                   "note": "CPU restatement of the reference (oracle/oracle.cpp), not the reference's wgpu GPU path; "
+                           "Mpix/s per iteration does not depend on the crop size"},
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": "port",
                          "sample": f"{side}x{side} crop of the same synthetic image, {steps} iterations, "
                                    "oracle/oracle.cpp (restated reference; Rust+wgpu reference not buildable here)"},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def parity_job(K, D, torch, proc, dev, w, h_total, k, blobs, world, rank, passes):
+    """One row-sharded k-means job (farthest-point init + `passes` passes) on all ranks; returns this
+    rank's (centroids, sums).  world == 1 runs the same job unsharded."""
+    rows = K.row_shards(h_total, world)[rank]
+    n_loc = w * (rows[1] - rows[0])
+    img = D.synth(proc, n_loc, first_pixel=w * rows[0], seed=SEED, blobs=blobs, device=dev)
+    work = D.convert(proc, img)
+    del img
+    job = D.Job(proc, work, w, rows[1] - rows[0], k, opts=K.Opts(max_dim=0, max_iter=passes, check_every=0))
+    if world > 1:
+        job.set_shard(w, h_total, rows[0])
+    job.init()
+    job.step(passes)
+    cent, sums = job.centroids(), job.sums()
+    job.close()
+    del work
+    torch.cuda.empty_cache()
+    return cent, sums
+
+
+def parity_check(K, D, torch, dist, proc, dev, world, rank):
+    """identical results at 1/2/4/8 GPUs.  Two sharded jobs — the headline shape
+    (8192 x 8192 per GPU, k = 8) and BASELINE config 4 (one 8192 x 8192 image, k = 256) — each with
+    its init and 16 passes: the k x 4 centroids and int64 sums must be bit-identical on every rank,
+    and equal to what rank 0 gets when it runs the same image alone, unsharded."""
+    out = {"ranks_identical": True, "equals_single_gpu": True, "jobs": []}
+    solo = None
+    for name, w, h_total, k, blobs in (("headline 8192 x (8192 N) k=8", W, H * world, K_CLUSTERS, BLOBS),
+                                       ("config 4: 8192 x 8192 k=256", W, H, 256, 512)):
+        cent, sums = parity_job(K, D, torch, proc, dev, w, h_total, k, blobs, world, rank, 16)
+        mine = torch.from_numpy(np.concatenate([cent.view(np.int32).astype(np.int64).ravel(), sums.ravel()])).to(dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        same = all(bool(torch.equal(allr[0], a)) for a in allr)
+        equal = None
+        if rank == 0:
+            # a second context without a communicator: the whole image on this GPU alone
+            solo = solo or K.ImageProcessor(dev.index)
+            c1, s1 = parity_job(K, D, torch, solo, dev, w, h_total, k, blobs, 1, 0, 16)
+            equal = bool(np.array_equal(c1.view(np.uint32), cent.view(np.uint32)) and np.array_equal(s1, sums))
+        flag = torch.tensor([1 if (equal is None or equal) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        equal = bool(int(flag[0]))
+        out["ranks_identical"] &= same
+        out["equals_single_gpu"] &= equal
+        out["jobs"].append({"job": name, "ranks_identical": same, "equals_single_gpu": equal, "passes": 16,
+                            "compared": "k x 4 centroids (bit patterns) and k x 4 int64 sums, all-gathered"})
+    if solo is not None:
+        solo.close()
+    return out
 
 
 def run_ours(args):
@@ -292,6 +347,7 @@ def run_ours(args):
     job4.close()
     del work4, img4
     torch.cuda.empty_cache()
+    parity = parity_check(K, D, torch, dist, proc, dev, world, rank) if world > 1 else None
     extras = run_extras(proc, K, D, torch, dev, world, rank, dist if world > 1 else None)
     extras["iteration_k256_8192"] = {"mpix_per_s_per_gpu": n / ms256 / 1e3, "ms_per_pass": ms256,
                                      "exact_path_pixels_per_pass": st256["slow_pixels"] / max(st256["passes"], 1),
@@ -329,7 +385,8 @@ def run_ours(args):
                              "plus a certificate; the binding resource is instruction issue under register-bank limits "
                              "(DESIGN.md 4.6)",
                      "issue_frac": (warp_inst * 32 / (step_ms * 1e-3) / fma_peak) if warp_inst else None,
-                     "issue_frac_what": "executed warp instructions of one launch (ncu, profiles/traffic.json) x 32 lanes / time / peak"}
+                     "issue_frac_what": "static instruction count: executed warp instructions of one launch (ncu capture in "
+                                        "profiles/traffic.json, not measured in this run) x 32 lanes / time / peak"}
         if world == 1:
             cpu_mpix, cpu_threads, cpu_sec = cpu_iteration_sample(2048, 3)
             cpu_baseline = {"value": cpu_mpix, "unit": "Mpix/s", "cores": cpu_threads, "kind": "port",
@@ -348,13 +405,18 @@ def run_ours(args):
                        "k": K_CLUSTERS, "bytes_per_px": BYTES_PER_PX, "l2": "work plane 1 GiB per GPU > 126 MB L2",
                        "exact_path_pixels_per_pass": stats["slow_pixels"] / max(stats["passes"], 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_lloyd<KT=8,KCAP=8,256 threads,4 px/thread,thread-private atomic slots,2 blocks/SM,table in the constant bank>",
+                         "traffic": traffic, "traffic_source": "static: profiles/traffic.json (ncu --set full capture of this kernel "
+                         "on this shape, committed with the profile; not measured in this run)", "peak_source": peak_src, "kernel": "k_lloyd<KT=8,KCAP=8,256 threads,4 px/thread,thread-private atomic slots,2 blocks/SM,table in the constant bank>",
                          "kernel_ms": step_ms},
             "roofline_fp32": fp32_roof,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": K_CLUSTERS * 16 + 64,
-                    "call": f"kmg_kmeans_palette(max_dim=0, {E2E_PASSES} passes) on a pinned host image", "steps": e2e_steps},
+                    "call": f"kmg_kmeans_palette(max_dim=0, {E2E_PASSES} passes) on a pinned host image", "steps": e2e_steps,
+                    "call_ms": e2e_s / e2e_steps * 1e3, "images_per_s": world * e2e_steps / e2e_s,
+                    "note": f"one call = one 268 MB upload + conversion + 7 init rounds + {E2E_PASSES} passes + read-back; "
+                            "Mpix/s counts every pass, images/s counts calls"},
             "gpu_launches": int(launches),
+            "parity_check": parity,
             "clocks": clocks,
             "extras": extras,
         }
@@ -362,6 +424,8 @@ def run_ours(args):
     proc.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not (parity["ranks_identical"] and parity["equals_single_gpu"]):
+        raise SystemExit("bench.py: multi-GPU parity check failed: " + json.dumps(parity))
 
 
 def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
@@ -466,13 +530,16 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
                                          "e2e_images_per_s": 1.0 / t_find, "e2e_mpix_per_s": w4 * h4 / t_find / 1e6}
     job64.close()
 
-    # ---- config 5: 1920x1080 frames, k=16 reduce + dither --------------------------------------------
-    nf = 192
+    # ---- config 5 as BASELINE states it: 4096 resident 1920x1080 frames, k=16 reduce + dither, the frames
+    # sharded over the N GPUs (strong scaling; no collective) -----------------------------------------
+    total_frames = 4096
+    lo, hi = K.frame_shards(total_frames, world)[rank]
+    nf = hi - lo
     frames = torch.empty((nf, 1080, 1920, 4), dtype=torch.uint8, device=dev)
     for f in range(nf):
-        D.synth(proc, 1920 * 1080, frame=rank * nf + f, seed=3, blobs=32, out=frames[f].view(-1, 4))
+        D.synth(proc, 1920 * 1080, frame=lo + f, seed=3, blobs=32, out=frames[f].view(-1, 4))
     outb = torch.empty_like(frames)
-    D.reduce_batch(proc, frames, 16, K.ReduceMode.Dither, out=outb)  # warm-up (workspace allocation)
+    D.reduce_batch(proc, frames[:64], 16, K.ReduceMode.Dither, out=outb[:64])  # warm-up (workspace allocation)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -480,8 +547,11 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
     _, _, passes = D.reduce_batch(proc, frames, 16, K.ReduceMode.Dither, out=outb)
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
-    entry = {"images_per_s": world * nf / dt, "frames_per_gpu": nf, "mean_passes": float(passes.mean()),
-             "launches": 2, "what": "kmg_dev_reduce_batch: one cluster launch + one remap launch for all frames"}
+    entry = {"images_per_s": total_frames / dt, "frames_total": total_frames, "frames_per_gpu": nf, "n_gpus": world,
+             "scaling": "strong", "seconds": dt, "mean_passes": float(passes.mean()), "launches": 2,
+             "resident_bytes_per_gpu": int(frames.numel()) * 2,
+             "what": "BASELINE config 5: 4096 synthetic 1080p frames resident in HBM, contiguous frame ranges per GPU "
+                     "(frame_shards), kmg_dev_reduce_batch: one cluster launch + one remap launch for the rank's frames"}
     hn = 96
     hin = K.pinned_empty((hn, 1080, 1920, 4))
     hin[...] = frames[:hn].cpu().numpy()
@@ -495,6 +565,7 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
     dt = max_over_ranks(time.perf_counter() - t0)
     entry["e2e_images_per_s"] = world * hn / dt
     entry["e2e_bytes_per_frame_each_way"] = 1920 * 1080 * 4
+    entry["e2e_gb_per_s_each_way_per_gpu"] = hn * 1920 * 1080 * 4 / dt / 1e9
     entry["e2e_what"] = f"kmg_reduce_batch on {hn} pinned host frames per GPU: chunked H2D / kernels / D2H pipeline"
     out["frames_1080p_k16_reduce_dither"] = entry
     return out

@@ -49,6 +49,7 @@ static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
 #define LV16(P, MINB, CT, ATOM) k_lloyd<16, 16, 256, P, true, MINB, CT, ATOM>, 16, 256, P, CT, (size_t)16 * 256 * 16
 // warp-specialised TMA ring (kmg_lloyd_ring.cuh): 8 consumer warps + 1 producer warp, P px per lane and stage, D stages
 #define LVR(P, D, MINB) k_lloyd_ring<8, 8, P, D, MINB>, 8, 288, P, true, (size_t)RingLayout<8, 8, P, D>::BYTES
+#define LVRF(P, D, MINB, F) k_lloyd_ring<8, 8, P, D, MINB, F>, 8, 288, P, true, (size_t)RingLayout<8, 8, P, D>::BYTES
 static const LloydVariant LLOYD_VARIANTS[] = {
     // k <= 8
     {LVR(2, 8, 2), "TMA ring 8 x 8 KiB, table resident in uniform registers, 8+1 warps, 2 blocks/SM"},
@@ -62,6 +63,11 @@ static const LloydVariant LLOYD_VARIANTS[] = {
     {LVR(4, 4, 2), "TMA ring 4 x 16 KiB, 2 blocks/SM"},
     {LVR(2, 4, 3), "TMA ring 4 x 8 KiB, 3 blocks/SM"},
     {LVR(8, 2, 2), "TMA ring 2 x 32 KiB, 2 blocks/SM"},
+    {LVRF(2, 8, 2, 1), "TMA ring 8 x 8 KiB, no evict-first hint"},
+    {LVRF(2, 8, 2, 2), "TMA ring 8 x 8 KiB, suspend hint"},
+    {LVRF(2, 8, 2, 4), "TMA ring 8 x 8 KiB, L2 prefetch"},
+    {LVRF(2, 8, 2, 6), "TMA ring 8 x 8 KiB, suspend hint + L2 prefetch"},
+    {LVRF(2, 4, 3, 6), "TMA ring 4 x 8 KiB, 3 blocks/SM, suspend hint + L2 prefetch"},
     // k <= 16
     {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
     {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},

@@ -46,10 +46,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Same, but a warp whose phase has not completed is suspended by the hardware for up to `ns`
+// nanoseconds per attempt instead of re-issuing the test (a spinning warp takes issue slots from
+// the warps that still have pixels to work on).
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(bar),
+      "r"(parity), "r"(ns)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+__device__ __forceinline__ void bulk_g2s_nohint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, UBLKCP).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
@@ -127,7 +151,9 @@ __device__ __noinline__ void ring_slow_pair(const CentRec* __restrict__ g_tab, u
   }
 }
 
-template <int KT, int CWARPS, int P, int D, int MINB>
+// FLAGS (experiments): 1 = no L2 evict-first hint on the copies, 2 = suspend-time hint on the waits,
+// 4 = the producer prefetches the tile 2 D stages ahead into L2
+template <int KT, int CWARPS, int P, int D, int MINB, int FLAGS = 0>
 __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     k_lloyd_ring(JobPtrs J, const float4* __restrict__ work, unsigned long long n, int color_space, int distributed_mode,
                  PeerXchg X, int cslot, unsigned int k_arg) {
@@ -181,10 +207,19 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     const unsigned long long gstep = (unsigned long long)gridDim.x * (BT * 16);
     for (unsigned int t = 0; t < my_tiles; ++t) {
       const unsigned int s = t & (D - 1);
-      if (t >= D) mbar_wait(empty_u32 + s * 8, ((t / D) - 1u) & 1u);
+      if (t >= D) {
+        if (FLAGS & 2)
+          mbar_wait_suspend(empty_u32 + s * 8, ((t / D) - 1u) & 1u, 1000u);
+        else
+          mbar_wait(empty_u32 + s * 8, ((t / D) - 1u) & 1u);
+      }
       if (lane == 0) {
         mbar_expect_tx(full_u32 + s * 8, L::STAGE_BYTES);
-        bulk_g2s(ring_u32 + s * L::STAGE_BYTES, gsrc, L::STAGE_BYTES, full_u32 + s * 8, policy);
+        if (FLAGS & 1)
+          bulk_g2s_nohint(ring_u32 + s * L::STAGE_BYTES, gsrc, L::STAGE_BYTES, full_u32 + s * 8);
+        else
+          bulk_g2s(ring_u32 + s * L::STAGE_BYTES, gsrc, L::STAGE_BYTES, full_u32 + s * 8, policy);
+        if ((FLAGS & 4) && t + 2 * D < my_tiles) bulk_prefetch_l2(gsrc + 2 * D * gstep, L::STAGE_BYTES);
       }
       gsrc += gstep;
     }
@@ -260,7 +295,12 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
       for (; u < u_stop; ++u) {
         const unsigned int t = u / PAIRS, sub = u % PAIRS;
         const unsigned int s = t & (D - 1);
-        if (sub == 0) mbar_wait(full_u32 + s * 8, (t / D) & 1u);
+        if (sub == 0) {
+          if (FLAGS & 2)
+            mbar_wait_suspend(full_u32 + s * 8, (t / D) & 1u, 1000u);
+          else
+            mbar_wait(full_u32 + s * 8, (t / D) & 1u);
+        }
         const uint32_t pair_addr = ring_lane_u32 + s * L::STAGE_BYTES + sub * 1024;
         const float4 va = lds128(pair_addr), vb = lds128(pair_addr + 512);
         const fast::PixCoef ca = fast::pix_coef(va.x, va.y, va.z, va.w);

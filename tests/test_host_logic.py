@@ -182,3 +182,59 @@ def test_header_is_plain_c_and_links(native_lib, tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out[:5] == ["256", "171", "2", "0", "1"]
     assert abs(float(out[5]) - 2.742) < 0.01  # L of #0a0a0a
+
+
+def _c_prototypes():
+    """name -> number of parameters, from include/kmeans_gpu.h."""
+    text = (ROOT / "include" / "kmeans_gpu.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for name, args in re.findall(r"\b(kmg_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", text):
+        args = args.strip()
+        protos[name] = 0 if args in ("", "void") else len(args.split(","))
+    return protos
+
+
+def test_rust_shim_matches_header():
+    """integration/rust cannot be compiled here (no cargo/rustc): check at least that
+    ffi.rs binds only functions the header declares, with the same number of parameters, that the
+    kmg_opts mirror has the header's fields in order, and that lib.rs keeps the reference's public
+    items (core/src/lib.rs:24-253) and calls nothing ffi.rs does not declare."""
+    rust = ROOT / "integration" / "rust" / "core"
+    ffi = (rust / "src" / "ffi.rs").read_text()
+    lib = (rust / "src" / "lib.rs").read_text()
+    protos = _c_prototypes()
+    block = ffi[ffi.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    block = re.sub(r"//.*", "", block)
+    bound = {}
+    for name, args in re.findall(r"pub fn (kmg_[a-z0-9_]+)\s*\(([^)]*)\)", block, flags=re.S):
+        args = [a for a in (x.strip() for x in args.split(",")) if a]
+        bound[name] = len(args)
+    assert len(bound) >= 15
+    for name, n in bound.items():
+        assert name in protos, f"ffi.rs binds {name}, which include/kmeans_gpu.h does not declare"
+        assert protos[name] == n, f"{name}: {n} parameters in ffi.rs, {protos[name]} in the header"
+    for need in ("kmg_create", "kmg_destroy", "kmg_kmeans_palette", "kmg_remap", "kmg_reduce", "kmg_resize", "kmg_last_error"):
+        assert need in bound
+    # kmg_opts field order
+    header = (ROOT / "include" / "kmeans_gpu.h").read_text()
+    hdr_fields = re.findall(r"^\s+(?:uint32_t|int32_t|float)\s+(\w+);", header[header.index("typedef struct kmg_opts"):header.index("} kmg_opts;")], flags=re.M)
+    rs_fields = re.findall(r"pub (\w+): [a-z0-9]+,", ffi[ffi.index("pub struct KmgOpts"):ffi.index("extern")])
+    assert hdr_fields == rs_fields and len(rs_fields) == 10
+    # every ffi:: call in lib.rs is declared in ffi.rs
+    for name in set(re.findall(r"ffi::(kmg_[a-z0-9_]+)", lib)):
+        assert name in bound, name
+    # the public surface of the reference crate is intact
+    for item in ("pub struct ImageProcessor", "pub async fn new() -> Result<Self>", "pub async fn palette<C: Container>(",
+                 "pub async fn find<C: Container>(", "pub async fn reduce<C: Container>(", "pub enum ColorSpace", "pub enum Algorithm",
+                 "pub enum ReduceMode", "pub use rgb::RGBA8;", "pub mod image;", "impl FromStr for ColorSpace",
+                 "pub fn convergence(&self) -> f32", "async fn kmeans_palette<C: Container>(", "async fn octree_palette<C: Container>("):
+        assert item in lib, item
+    assert "Replace = 0" in lib and "Dither = 1" in lib and "Meld = 2" in lib and "Lab = 0" in lib and "Rgb = 1" in lib
+    build = (rust / "build.rs").read_text()
+    assert "arch=compute_100a,code=sm_100a" in build and "cargo:rustc-link-lib=dylib=kmeans_gpu" in build
+    csrc = {p.name for p in (ROOT / "kmeans-gpu_b200" / "csrc").glob("*.cu*")} | {"kmg_host.cpp"}
+    for f in re.findall(r'"(kmg_[a-z_]+\.(?:cuh|cu|cpp))"', build):
+        assert f in csrc, f"build.rs names {f}, which is not in kmeans-gpu_b200/csrc"
+    assert {p.name for p in (ROOT / "kmeans-gpu_b200" / "csrc").glob("*.cuh")} <= set(re.findall(r'"(kmg_[a-z_]+\.cuh)"', build))
