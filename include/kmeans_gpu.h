@@ -220,6 +220,20 @@ int kmg_dev_fast_lab_error(kmg_ctx* ctx, float* max_err_out);
 /* Measured FP32 (non-tensor) peak of the device in fused multiply-adds per second (x 2 = FLOP/s):
  * the FP32 side of the roofline bench.py reports next to the HBM side. */
 int kmg_dev_fp32_peak(kmg_ctx* ctx, double* fma_per_second_out);
+/* Audit of the near-tie certificate (test hook; tests/test_gpu_parity.py::test_certificate_audit_*).
+ * The production searches trust a certified label without evaluating the reference distance; this
+ * runs the same device functions on every pixel, also scans all k centroids with the reference's
+ * arithmetic and order (core/shaders/find_centroid.wgsl:29-41), and returns in *wrong_out the number
+ * of pixels whose certified label differs from that scan (any value but 0 is a bug in an error
+ * bound) and in *uncertified_out the pixels production would hand to its exact path.
+ *   search  0: 8-entry table, all scores kept   1: 16-entry table   2: chunked search, any k
+ *           3: the resident-table search of the k <= 8 Lloyd pass (kmg_lloyd_ring.cuh)
+ *   mode    0: Lloyd pass / assignment — d_work is the exact work plane of the w*h pixels
+ *           1: remap, replace   2: remap, ordered dither — d_rgba is the RGBA8 image (fast Lab in the
+ *              kernel; the reference label is the scan of the exact pixel + dither offset) */
+int kmg_dev_audit(kmg_ctx* ctx, const float* d_work, const uint8_t* d_rgba, uint32_t w, uint32_t h,
+                  const float* centroids_host, uint32_t k, int color_space, int search, int mode, uint64_t* wrong_out,
+                  uint64_t* uncertified_out, void* stream);
 /* Number of kernels this library launched on behalf of ctx since creation. */
 uint64_t kmg_launch_count(kmg_ctx* ctx);
 

@@ -12,6 +12,7 @@ const SOURCES: &[&str] = &["kmg_api.cu", "kmg_host.cpp"];
 const HEADERS: &[&str] = &[
     "kmg_kernels.cuh",
     "kmg_lloyd_ring.cuh",
+    "kmg_audit.cuh",
     "kmg_small.cuh",
     "kmg_math.cuh",
 ];

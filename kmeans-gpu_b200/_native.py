@@ -90,6 +90,7 @@ SIGNATURES = {
     "kmg_dev_srgb_table": (C.c_int, [_vp, _f32p]),
     "kmg_dev_fast_lab_error": (C.c_int, [_vp, _f32p]),
     "kmg_dev_fp32_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "kmg_dev_audit": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _f32p, C.c_uint32, C.c_int, C.c_int, C.c_int, _u64p, _u64p, _vp]),
     "kmg_launch_count": (C.c_uint64, [_vp]),
     "kmg_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "kmg_free_pinned": (None, [_vp]),

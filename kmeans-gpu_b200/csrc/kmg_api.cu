@@ -21,6 +21,7 @@
 #include "kmg_kernels.cuh"
 #include "kmg_small.cuh"
 #include "kmg_lloyd_ring.cuh"
+#include "kmg_audit.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -68,6 +69,11 @@ static const LloydVariant LLOYD_VARIANTS[] = {
     {LVRF(2, 8, 2, 4), "TMA ring 8 x 8 KiB, L2 prefetch"},
     {LVRF(2, 8, 2, 6), "TMA ring 8 x 8 KiB, suspend hint + L2 prefetch"},
     {LVRF(2, 4, 3, 6), "TMA ring 4 x 8 KiB, 3 blocks/SM, suspend hint + L2 prefetch"},
+    {LVRF(2, 8, 2, 8), "TMA ring 8 x 8 KiB, memory side alone (timing experiment, wrong sums)"},
+    {LVRF(2, 8, 2, 16), "TMA ring 8 x 8 KiB, compute side alone (timing experiment, wrong sums)"},
+    {LVRF(2, 4, 2, 8), "TMA ring 4 x 8 KiB, memory side alone (timing experiment, wrong sums)"},
+    {LVRF(2, 8, 2, 32), "TMA ring 8 x 8 KiB, no slot reductions (timing experiment, wrong sums)"},
+    {LVRF(2, 8, 2, 64), "TMA ring 8 x 8 KiB, one slot reduction per pixel (timing experiment, wrong sums)"},
     // k <= 16
     {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
     {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
@@ -1176,6 +1182,69 @@ extern "C" int kmg_dev_assign(kmg_ctx* ctx, const float* d_work, uint64_t n, con
   LAUNCHED(ctx);
   CHECK_LAUNCH();
   CU(cudaStreamSynchronize(s));
+  return KMG_OK;
+}
+
+template <int SEARCH>
+static int launch_audit(kmg_job* j, const float4* work, const uint32_t* rgba, uint32_t w, unsigned long long n, int mode,
+                        unsigned long long* d_counters, cudaStream_t s) {
+  kmg_ctx* ctx = j->ctx;
+  const unsigned int kp = (SEARCH == 0 || SEARCH == 3) ? 8u : (SEARCH == 1 ? 16u : pad32(j->k));
+  const size_t smem = tab_smem_bytes(kp);
+  const int grid = ctx->sms * (smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
+  if (mode == 0) {
+    CU(cudaFuncSetAttribute(k_audit<SEARCH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_audit<SEARCH, 0><<<grid, 256, smem, s>>>(j->P, work, rgba, w, n, j->color_space, ctx->d_lut, d_counters);
+  } else if (mode == 1) {
+    CU(cudaFuncSetAttribute(k_audit<SEARCH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_audit<SEARCH, 1><<<grid, 256, smem, s>>>(j->P, work, rgba, w, n, j->color_space, ctx->d_lut, d_counters);
+  } else {
+    CU(cudaFuncSetAttribute(k_audit<SEARCH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_audit<SEARCH, 2><<<grid, 256, smem, s>>>(j->P, work, rgba, w, n, j->color_space, ctx->d_lut, d_counters);
+  }
+  LAUNCHED(ctx);
+  CHECK_LAUNCH();
+  return KMG_OK;
+}
+
+extern "C" int kmg_dev_audit(kmg_ctx* ctx, const float* d_work, const uint8_t* d_rgba, uint32_t w, uint32_t h,
+                             const float* cent, uint32_t k, int cs, int search, int mode, uint64_t* wrong_out,
+                             uint64_t* uncertified_out, void* stream) {
+  if (!ctx || !cent || !wrong_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: NULL argument");
+  if (mode < 0 || mode > 2 || search < 0 || search > 3) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: unknown search %d / mode %d", search, mode);
+  if (mode == 0 ? !d_work : !d_rgba) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: mode %d needs the %s", mode, mode == 0 ? "work plane" : "RGBA8 image");
+  TRY(validate_dims(w, h, k));
+  if (((search == 0 || search == 3) && k > 8) || (search == 1 && k > 16))
+    return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: search %d holds at most %d centroids", search, search == 1 ? 16 : 8);
+  if (cs != KMG_LAB && cs != KMG_RGB) return fail(KMG_ERR_BAD_ARG, "unknown colour space %d", cs);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick_stream(ctx, stream);
+  TempJob t;
+  TRY(t.setup(ctx, w, h, cent, k, cs, s));
+  TRY(launch_prepare(&t.job, true, s));  // table, dither threshold, palette
+  struct Scratch : Buf {
+    ~Scratch() { release(); }
+  } counters;
+  TRY(counters.ensure(16));
+  CU(cudaMemsetAsync(counters.p, 0, 16, s));
+  const unsigned long long n = (unsigned long long)w * h;
+  unsigned long long* dc = (unsigned long long*)counters.p;
+  const float4* work = (const float4*)d_work;
+  const uint32_t* rgba = (const uint32_t*)d_rgba;
+  int r = search == 0   ? launch_audit<0>(&t.job, work, rgba, w, n, mode, dc, s)
+          : search == 1 ? launch_audit<1>(&t.job, work, rgba, w, n, mode, dc, s)
+          : search == 2 ? launch_audit<2>(&t.job, work, rgba, w, n, mode, dc, s)
+                        : launch_audit<3>(&t.job, work, rgba, w, n, mode, dc, s);
+  if (r != KMG_OK) {
+    cudaStreamSynchronize(s);
+    return r;
+  }
+  unsigned long long h_c[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h_c, dc, 16, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(KMG_ERR_CUDA, "kmg_dev_audit: %s", cudaGetErrorString(e));
+  *wrong_out = h_c[0];
+  if (uncertified_out) *uncertified_out = h_c[1];
   return KMG_OK;
 }
 

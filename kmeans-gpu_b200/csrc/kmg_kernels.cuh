@@ -1265,6 +1265,36 @@ __device__ __noinline__ float4 remap_exact_pixel(uint32_t v, const float* __rest
   return e;
 }
 
+// The approximate pixel of the remap kernels: fast Lab (or v / 255), plus the ordered-dither offset
+// of cell (x % 4, y % 4) in MODE 1, and the approximate chroma the score takes.
+template <int MODE>
+__device__ __forceinline__ void remap_fast_pixel(uint32_t v, const float* __restrict__ lut, int color_space, float thr,
+                                                 unsigned int xi, unsigned int yi, float& L, float& a, float& b, float& C,
+                                                 float& off) {
+  if (color_space == 0) {
+    float3 lab = fast::lin100_to_lab(lut[v & 255u], lut[(v >> 8) & 255u], lut[(v >> 16) & 255u]);
+    L = lab.x;
+    a = lab.y;
+    b = lab.z;
+  } else {
+    L = (float)(v & 255u) * (1.0f / 255.0f);
+    a = (float)((v >> 8) & 255u) * (1.0f / 255.0f);
+    b = (float)((v >> 16) & 255u) * (1.0f / 255.0f);
+  }
+  off = 0.0f;
+  if (MODE == 1) {
+    // index_matrix[x % 4 + 4 * (y % 4)] / 16 - 0.5 (mix_colors.wgsl:14-17,21-27,70); the sixteen
+    // 4-bit entries sit in one 64-bit constant (no divergent constant-bank load)
+    const unsigned int cell = (xi & 3u) + ((yi & 3u) << 2);
+    float iv = (float)((unsigned int)(BAYER_NIBBLES >> (4u * cell)) & 15u) * 0.0625f - 0.5f;
+    off = fmul(thr, iv);
+    L += off;
+    a += off;
+    b += off;
+  }
+  C = fast::sqrt_approx(fmaf(a, a, b * b));
+}
+
 template <int MODE, int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t* __restrict__ rgba, unsigned int w,
                                                    unsigned long long n, int color_space,
@@ -1328,37 +1358,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_remap(JobPtrs J0, const uint32_t
     }
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      float L, a, b;
-      if (color_space == 0) {
-        float3 lab = fast::lin100_to_lab(lut[v[i] & 255u], lut[(v[i] >> 8) & 255u], lut[(v[i] >> 16) & 255u]);
-        L = lab.x;
-        a = lab.y;
-        b = lab.z;
-      } else {
-        L = (float)(v[i] & 255u) * (1.0f / 255.0f);
-        a = (float)((v[i] >> 8) & 255u) * (1.0f / 255.0f);
-        b = (float)((v[i] >> 16) & 255u) * (1.0f / 255.0f);
-      }
-      off[i] = 0.0f;
+      unsigned int xi = x + i, yi = y;
       if (MODE == 1) {
-        unsigned int xi = x + i, yi = y;
         while (xi >= w) {  // group straddles a row end (w % 4 != 0)
           xi -= w;
           ++yi;
         }
-        // index_matrix[x % 4 + 4 * (y % 4)] / 16 - 0.5 (mix_colors.wgsl:14-17,21-27,70); the sixteen
-        // 4-bit entries sit in one 64-bit constant (no divergent constant-bank load)
-        const unsigned int cell = (xi & 3u) + ((yi & 3u) << 2);
-        float iv = (float)((unsigned int)(BAYER_NIBBLES >> (4u * cell)) & 15u) * 0.0625f - 0.5f;
-        off[i] = fmul(thr, iv);
-        L += off[i];
-        a += off[i];
-        b += off[i];
       }
-      px.L[i] = L;
-      px.a[i] = a;
-      px.b[i] = b;
-      px.C[i] = fast::sqrt_approx(fmaf(a, a, b * b));
+      remap_fast_pixel<MODE>(v[i], lut, color_space, thr, xi, yi, px.L[i], px.a[i], px.b[i], px.C[i], off[i]);
     }
     const float conv_k = color_space == 0 ? fast::LAB_ERR : fast::RGB_ERR;  // |approximate pixel - exact pixel|
     float eps[P];

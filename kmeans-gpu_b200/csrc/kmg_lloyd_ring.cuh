@@ -22,10 +22,6 @@
 
 namespace kmg {
 
-#ifdef RING_DEBUG
-__device__ float g_dbg[64 * 32];
-#endif
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -128,6 +124,65 @@ __device__ __forceinline__ void slot_add(uint32_t addr, float L, float a, float 
       : "memory");
 }
 
+// The certified search of one pixel pair against the resident table (tq[j][1] carries -Lc * 2^9).
+// Returns, per pixel, the bits of 2^23 + V with V = sum_j (KT + j) * STRIDE * [s_j <= min + eps]:
+// exactly one score within eps of the minimum  <=>  (V & CERT_MASK) == CERT_ONE, and then
+// V & IDX_MASK = idx * STRIDE, the byte offset of cluster idx's slot.
+template <int KT, unsigned int STRIDE>
+struct RingCert {
+  static constexpr unsigned int IDX_MASK = (KT - 1) * STRIDE;
+  static constexpr unsigned int CERT_MASK = 0x7fffffu & ~(unsigned int)(KT * STRIDE - 1);
+  static constexpr unsigned int CERT_ONE = KT * STRIDE;
+};
+template <int KT, unsigned int STRIDE>
+__device__ __forceinline__ void ring_pair_search(const float4& va, const float4& vb, const float (&tq)[KT][6], float lmax_u,
+                                                 float cmax_v, unsigned int& ua, unsigned int& ub) {
+  constexpr float TOTAL = (float)(KT * KT + KT * (KT - 1) / 2);  // sum of all weights (KT + j)
+  constexpr float WSCALE = (float)STRIDE;
+  const fast::PixCoef ca = fast::pix_coef(va.x, va.y, va.z, va.w);
+  const fast::PixCoef cb = fast::pix_coef(vb.x, vb.y, vb.z, vb.w);
+  fast::f32x2 pp[5];
+  pack_coefs(ca, cb, pp);
+  // L travels as L * 2^-9 against a table entry scaled by 2^9 (both exact): the pair then is the
+  // result of two multiplications — a pair merely put together from the two loads is cloned by
+  // ptxas before almost every use (ten moves per pixel pair)
+  const float la = va.x * 0.001953125f, lb = vb.x * 0.001953125f;
+  pp[0] = fast::pack2(la, lb);
+  float sa[KT], sb[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) fast::unpack2(score2(pp, tq[j]), sa[j], sb[j]);
+  float ma = fast::min3(sa[0], sa[1], sa[2]), mb = fast::min3(sb[0], sb[1], sb[2]);
+  ma = fast::min3(ma, sa[3], sa[4]);
+  mb = fast::min3(mb, sb[3], sb[4]);
+  ma = fast::min3(ma, sa[5], sa[6]);
+  mb = fast::min3(mb, sb[5], sb[6]);
+  ma = fminf(ma, sa[7]);
+  mb = fminf(mb, sb[7]);
+  // threshold = minimum + fast::score_eps, the addition folded into the last FMA
+  // (|L| * 2^-9.5 = |L * 2^-9| * 2^-0.5)
+  const float ua_ = fmaf(fabsf(la), 0.70710678f, lmax_u), va_ = fmaf(va.w, 0.001953125f, cmax_v);
+  const float ub_ = fmaf(fabsf(lb), 0.70710678f, lmax_u), vb_ = fmaf(vb.w, 0.001953125f, cmax_v);
+  const float ta = fmaf(ua_, ua_, fmaf(va_, va_, ma)), tb = fmaf(ub_, ub_, fmaf(vb_, vb_, mb));
+  // V = sum_j (KT + j) * stride * [s_j <= t]: exactly one score within eps of the minimum  <=>
+  // V == (KT + idx) * stride, and then V & IDX_MASK is the byte offset of cluster idx's slot
+  fast::f32x2 acc0 = fast::pack2(8388608.0f + TOTAL * WSCALE, 8388608.0f + TOTAL * WSCALE);
+  fast::f32x2 acc1 = fast::pack2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    const float fa = sa[j] > ta ? 1.0f : 0.0f;
+    const float fb = sb[j] > tb ? 1.0f : 0.0f;
+    const float w = -(float)(KT + j) * WSCALE;
+    if (j & 1)
+      acc1 = fast::fma2(fast::pack2(fa, fb), fast::pack2(w, w), acc1);
+    else
+      acc0 = fast::fma2(fast::pack2(fa, fb), fast::pack2(w, w), acc0);
+  }
+  float Va, Vb;
+  fast::unpack2(fast::add2(acc0, acc1), Va, Vb);
+  ua = __float_as_uint(Va);
+  ub = __float_as_uint(Vb);
+}
+
 // The exact path for the pixel pair that left the hot loop (cold; every lane of the warp calls it).
 // The hot loop has already added every pixel to the slot its flag sum pointed at (hit_a / hit_b,
 // byte offsets of a cluster): an uncertified pixel is taken out of that slot again and put into the
@@ -152,7 +207,10 @@ __device__ __noinline__ void ring_slow_pair(const CentRec* __restrict__ g_tab, u
 }
 
 // FLAGS (experiments): 1 = no L2 evict-first hint on the copies, 2 = suspend-time hint on the waits,
-// 4 = the producer prefetches the tile 2 D stages ahead into L2
+// 4 = the producer prefetches the tile 2 D stages ahead into L2,
+// 8 = memory side alone (consumers wait, touch the stage and release it: wrong sums, timing only),
+// 16 = compute side alone (only the first D tiles are ever copied, nobody waits: wrong sums, timing only),
+// 32 = no slot reductions, 64 = one slot reduction per pixel (wrong sums, timing only)
 template <int KT, int CWARPS, int P, int D, int MINB, int FLAGS = 0>
 __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     k_lloyd_ring(JobPtrs J, const float4* __restrict__ work, unsigned long long n, int color_space, int distributed_mode,
@@ -205,7 +263,7 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     const uint64_t policy = l2_evict_first_policy();
     const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(work) + (unsigned long long)blockIdx.x * (BT * 16);
     const unsigned long long gstep = (unsigned long long)gridDim.x * (BT * 16);
-    for (unsigned int t = 0; t < my_tiles; ++t) {
+    for (unsigned int t = 0; t < ((FLAGS & 16) ? min(my_tiles, (unsigned int)D) : my_tiles); ++t) {
       const unsigned int s = t & (D - 1);
       if (t >= D) {
         if (FLAGS & 2)
@@ -279,11 +337,8 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
 
     // |v| < 2^7 colour units -> |fixed| < 2^22: 480 pixels per slot stay below 2^31
     constexpr unsigned int FLUSH_PX = 480;
-    constexpr float TOTAL = (float)(KT * KT + KT * (KT - 1) / 2);  // sum of all weights (KT + j)
-    constexpr float WSCALE = (float)(CTHREADS * 4);                 // slot stride of a cluster in bytes
-    constexpr unsigned int IDX_MASK = (KT - 1) * CTHREADS * 4;
-    constexpr unsigned int CERT_MASK = 0x7fffffu & ~(unsigned int)(KT * CTHREADS * 4 - 1);
-    constexpr unsigned int CERT_ONE = KT * CTHREADS * 4;
+    using RC = RingCert<KT, CTHREADS * 4>;  // slot stride of a cluster in bytes
+    constexpr unsigned int IDX_MASK = RC::IDX_MASK, CERT_MASK = RC::CERT_MASK, CERT_ONE = RC::CERT_ONE;
     const unsigned int my_pairs = my_tiles * PAIRS;
 
     unsigned int u = 0;  // pixel pairs of this lane done so far; tile = u / PAIRS
@@ -295,7 +350,7 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
       for (; u < u_stop; ++u) {
         const unsigned int t = u / PAIRS, sub = u % PAIRS;
         const unsigned int s = t & (D - 1);
-        if (sub == 0) {
+        if (sub == 0 && (!(FLAGS & 16) || t < D)) {
           if (FLAGS & 2)
             mbar_wait_suspend(full_u32 + s * 8, (t / D) & 1u, 1000u);
           else
@@ -303,69 +358,32 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
         }
         const uint32_t pair_addr = ring_lane_u32 + s * L::STAGE_BYTES + sub * 1024;
         const float4 va = lds128(pair_addr), vb = lds128(pair_addr + 512);
-        const fast::PixCoef ca = fast::pix_coef(va.x, va.y, va.z, va.w);
-        const fast::PixCoef cb = fast::pix_coef(vb.x, vb.y, vb.z, vb.w);
-        fast::f32x2 pp[5];
-        pack_coefs(ca, cb, pp);
-        // L travels as L * 2^-9 against a table entry scaled by 2^9 (both exact): the pair then is the
-        // result of two multiplications — a pair merely put together from the two loads is cloned by
-        // ptxas before almost every use (ten moves per pixel pair)
-        const float la = va.x * 0.001953125f, lb = vb.x * 0.001953125f;
-        pp[0] = fast::pack2(la, lb);
-        float sa[KT], sb[KT];
-#pragma unroll
-        for (int j = 0; j < KT; ++j) fast::unpack2(score2(pp, tq[j]), sa[j], sb[j]);
-        float ma = fast::min3(sa[0], sa[1], sa[2]), mb = fast::min3(sb[0], sb[1], sb[2]);
-        ma = fast::min3(ma, sa[3], sa[4]);
-        mb = fast::min3(mb, sb[3], sb[4]);
-        ma = fast::min3(ma, sa[5], sa[6]);
-        mb = fast::min3(mb, sb[5], sb[6]);
-        ma = fminf(ma, sa[7]);
-        mb = fminf(mb, sb[7]);
-        // threshold = minimum + fast::score_eps, the addition folded into the last FMA
-        // (|L| * 2^-9.5 = |L * 2^-9| * 2^-0.5)
-        const float ua_ = fmaf(fabsf(la), 0.70710678f, lmax_u), va_ = fmaf(va.w, 0.001953125f, cmax_v);
-        const float ub_ = fmaf(fabsf(lb), 0.70710678f, lmax_u), vb_ = fmaf(vb.w, 0.001953125f, cmax_v);
-        const float ta = fmaf(ua_, ua_, fmaf(va_, va_, ma)), tb = fmaf(ub_, ub_, fmaf(vb_, vb_, mb));
-        // V = sum_j (KT + j) * stride * [s_j <= t]: exactly one score within eps of the minimum  <=>
-        // V == (KT + idx) * stride, and then V & IDX_MASK is the byte offset of cluster idx's slot
-        fast::f32x2 acc0 = fast::pack2(8388608.0f + TOTAL * WSCALE, 8388608.0f + TOTAL * WSCALE);
-        fast::f32x2 acc1 = fast::pack2(0.0f, 0.0f);
-#pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          const float fa = sa[j] > ta ? 1.0f : 0.0f;
-          const float fb = sb[j] > tb ? 1.0f : 0.0f;
-          const float w = -(float)(KT + j) * WSCALE;
-          if (j & 1)
-            acc1 = fast::fma2(fast::pack2(fa, fb), fast::pack2(w, w), acc1);
-          else
-            acc0 = fast::fma2(fast::pack2(fa, fb), fast::pack2(w, w), acc0);
+        if (FLAGS & 8) {
+          if (va.x + vb.x == 12345.678f) slow++;
+          if (sub == PAIRS - 1 && lane == 0) mbar_arrive(empty_u32 + s * 8);
+          continue;
         }
-        float Va, Vb;
-        fast::unpack2(fast::add2(acc0, acc1), Va, Vb);
-        const unsigned int ua = __float_as_uint(Va), ub = __float_as_uint(Vb);
+        unsigned int ua, ub;
+        ring_pair_search<KT, CTHREADS * 4>(va, vb, tq, lmax_u, cmax_v, ua, ub);
         const bool cert_a = (ua & CERT_MASK) == CERT_ONE, cert_b = (ub & CERT_MASK) == CERT_ONE;
-#ifdef RING_DEBUG
-        if (blockIdx.x == 0 && warp == 0 && u == 0) {
-          float* d = g_dbg + lane * 64;
-          d[0] = va.x; d[1] = va.y; d[2] = va.z; d[3] = va.w;
-          for (int j = 0; j < 8; ++j) d[4 + j] = sa[j];
-          d[12] = ma; d[13] = ta; d[14] = Va; d[15] = la;
-          for (int j = 0; j < 6; ++j) d[16 + j] = tq[0][j];
-          d[22] = lmax_u; d[23] = cmax_v; d[24] = __uint_as_float(ua);
-        }
-#endif
         // every pixel goes to the slot its flag sum points at; the rare uncertified one is moved by
         // the exact path below (no predicate, no branch around the reductions)
+        if (FLAGS & 32) {  // timing experiment: no accumulation at all (wrong sums)
+          if ((ua ^ ub) == 0x12345u) slow++;
+        } else if (FLAGS & 64) {  // timing experiment: one reduction per pixel instead of four (wrong sums)
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((ua & IDX_MASK) | slot_tid_u32), "r"(__float_as_uint(va.x)) : "memory");
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((ub & IDX_MASK) | slot_tid_u32), "r"(__float_as_uint(vb.x)) : "memory");
+        } else {
         slot_add<L::SLOT_SPAN>((ua & IDX_MASK) | slot_tid_u32, va.x, va.y, va.z);
         slot_add<L::SLOT_SPAN>((ub & IDX_MASK) | slot_tid_u32, vb.x, vb.y, vb.z);
+        }
         if (__any_sync(0xffffffffu, !(cert_a && cert_b))) {
           need = (cert_a ? 0u : 1u) | (cert_b ? 0u : 2u);
           hit_a = ua;
           hit_b = ub;
           break;
         }
-        if (sub == PAIRS - 1 && lane == 0) mbar_arrive(empty_u32 + s * 8);  // stage consumed by this warp
+        if (sub == PAIRS - 1 && lane == 0 && !(FLAGS & 16)) mbar_arrive(empty_u32 + s * 8);  // stage consumed by this warp
       }
       // ---- cold: exact path of the pair that left the loop, slot flush ------------------------------
       if (u < u_stop) {
@@ -404,7 +422,16 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
   __syncthreads();
   if (s_last) {
     __threadfence();
-    finalize_pass<THREADS>(J, color_space, distributed_mode, X);
+    if (FLAGS & (8 | 16 | 32 | 64)) {
+      // timing experiments produce wrong sums: drop them, keep the centroids, count the pass
+      for (unsigned int c = tid; c < J.acc_copies * k * 4; c += THREADS) J.acc[c] = 0;
+      if (tid == 0) {
+        st->passes += 1;
+        st->ticket = 0;
+      }
+    } else {
+      finalize_pass<THREADS>(J, color_space, distributed_mode, X);
+    }
   }
 }
 

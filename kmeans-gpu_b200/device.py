@@ -86,6 +86,21 @@ def fast_lab_error(proc: ImageProcessor) -> float:
     return float(v.value)
 
 
+def audit(proc: ImageProcessor, centroids: np.ndarray, search: int, mode: int, work: torch.Tensor | None = None,
+          rgba: torch.Tensor | None = None, w: int | None = None, h: int | None = None,
+          color_space: ColorSpace = ColorSpace.Lab, stream=None) -> tuple[int, int]:
+    """Certificate audit (kmg_dev_audit): returns (certified-but-wrong pixels, uncertified pixels)."""
+    cent = np.ascontiguousarray(centroids, np.float32).reshape(-1, 4)
+    n = work.shape[0] if work is not None else rgba.numel() // 4
+    if w is None:
+        w, h = n, 1
+    wrong, unc = C.c_uint64(0), C.c_uint64(0)
+    _native.check(proc._lib.kmg_dev_audit(proc.ctx, _dptr(work) if work is not None else None,
+                                          _dptr(rgba) if rgba is not None else None, w, h, _f32p(cent), cent.shape[0],
+                                          int(color_space), search, mode, C.byref(wrong), C.byref(unc), _stream_ptr(stream)))
+    return int(wrong.value), int(unc.value)
+
+
 def fp32_peak(proc: ImageProcessor) -> float:
     """Measured non-tensor FP32 peak of the device, fused multiply-adds per second."""
     v = C.c_double(0)

@@ -731,3 +731,79 @@ def test_full_size_properties_8192(proc, D, K, oracle, torch):
     assert set(got.tolist()) <= set(pal.view(np.uint32).ravel().tolist())
     for j in (job, j0, j1):
         j.close()
+
+
+# ---- certificate audit: every certified label is the reference scan's, on ALL 2^24 colours -----------
+
+def _audit_palettes(K, rng, k, n):
+    """n palettes of k centroids (Lab): random in-gamut colours with sub-LSB jitter, near-duplicates,
+    saturated primaries, near-greys — the shapes that stress the error bound."""
+    out = []
+    for i in range(n):
+        kind = i % 4
+        cols = rng.integers(0, 256, (k, 4), dtype=np.uint8)
+        if kind == 2:  # saturated: every channel 0 or 255 (plus a few mid values so that k colours exist)
+            cols[:, :3] = np.where(rng.random((k, 3)) < 0.8, rng.integers(0, 2, (k, 3)) * 255, cols[:, :3])
+        if kind == 3:  # near-grey: r ~ g ~ b within one or two levels
+            g = rng.integers(0, 256, (k, 1))
+            cols[:, :3] = np.clip(g + rng.integers(-2, 3, (k, 3)), 0, 255)
+        cols[:, 3] = 255
+        cent = K.fixed_centroids(cols, K.ColorSpace.Lab)
+        if kind != 2:  # k-means centroids are means, not 8-bit colours
+            cent[:, :3] += rng.normal(0, 0.2, (k, 3)).astype(np.float32)
+        if kind == 1 and k >= 2:  # near-duplicates: half of the palette sits 1e-4 .. 1e-2 next to the other half
+            h = k // 2
+            cent[h:2 * h, :3] = cent[:h, :3] + rng.choice([1e-4, 1e-3, 1e-2], (h, 1)).astype(np.float32) * \
+                rng.choice([-1.0, 1.0], (h, 3)).astype(np.float32)
+        cent[:, 3] = 1.0
+        out.append(cent)
+    return out
+
+
+def test_certificate_audit_all_colours(proc, D, K, torch):
+    """The production searches trust a certified label without evaluating the reference distance.
+    On all 2^24 sRGB colours x 204 palettes (k = 2 ... 700) every search (8- and 16-entry tables,
+    chunked, the resident-table search of the k <= 8 Lloyd pass) in every role (Lloyd on the exact
+    plane, remap replace, remap dither on the fast Lab) must certify only labels equal to the
+    reference's in-order scan (find_centroid.wgsl:29-41).  kmg_dev_audit counts the exceptions."""
+    v = torch.arange(1 << 24, dtype=torch.int32, device="cuda")
+    img = (v | (255 << 24)).view(torch.uint8).view(4096, 4096, 4)
+    work = D.convert(proc, img)
+    rng = np.random.default_rng(2024)
+    total = {"audits": 0, "uncertified": 0}
+    plan = {2: 40, 8: 52, 16: 40, 64: 32, 256: 25, 700: 15}
+    assert sum(plan.values()) >= 200
+    for k, n_pal in plan.items():
+        searches = ([0, 3] if k <= 8 else []) + ([1] if k <= 16 else []) + [2]
+        for pal_i, cent in enumerate(_audit_palettes(K, rng, k, n_pal)):
+            for mode in (0, 1, 2):
+                for search in searches:
+                    if search == 3 and mode != 0:
+                        continue  # the resident-table search only exists in the Lloyd pass
+                    if mode == 0:
+                        wrong, unc = D.audit(proc, cent, search, 0, work=work, w=4096, h=4096)
+                    else:
+                        wrong, unc = D.audit(proc, cent, search, mode, rgba=img, w=4096, h=4096)
+                    assert wrong == 0, (k, mode, search, wrong, cent.tolist())
+                    if pal_i % 4 == 0:  # random palettes: the fast path does the work (near-duplicate palettes
+                        assert unc < (0.05 if k <= 64 else 0.2) * (1 << 24), (k, mode, search, unc)  # legitimately send everything to the exact path)
+                    total["audits"] += 1
+                    total["uncertified"] += unc
+    assert total["audits"] >= 600
+
+
+def test_certificate_audit_rgb_colour_space(proc, D, K, torch):
+    v = torch.arange(1 << 24, dtype=torch.int32, device="cuda")
+    img = (v | (255 << 24)).view(torch.uint8).view(4096, 4096, 4)
+    work = D.convert(proc, img, K.ColorSpace.Rgb)
+    rng = np.random.default_rng(5)
+    for k in (2, 8, 16, 40):
+        for _ in range(4):
+            cent = np.ones((k, 4), np.float32)
+            cent[:, :3] = rng.random((k, 3), dtype=np.float32)
+            searches = ([0, 3] if k <= 8 else []) + ([1] if k <= 16 else []) + [2]
+            for search in searches:
+                assert D.audit(proc, cent, search, 0, work=work, w=4096, h=4096, color_space=K.ColorSpace.Rgb)[0] == 0
+                if search != 3:
+                    for mode in (1, 2):
+                        assert D.audit(proc, cent, search, mode, rgba=img, w=4096, h=4096, color_space=K.ColorSpace.Rgb)[0] == 0
