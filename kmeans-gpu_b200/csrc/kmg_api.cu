@@ -53,7 +53,7 @@ static constexpr size_t LLOYD32_SMEM = (32 / 8) * CHUNK_BYTES + 32 * 128 * 16;
 #define LVRF(P, D, MINB, F) k_lloyd_ring<8, 8, P, D, MINB, F>, 8, 288, P, true, (size_t)RingLayout<8, 8, P, D>::BYTES
 static const LloydVariant LLOYD_VARIANTS[] = {
     // k <= 8
-    {LVR(2, 8, 2), "TMA ring 8 x 8 KiB, table resident in uniform registers, 8+1 warps, 2 blocks/SM"},
+    {LVR(4, 4, 2), "TMA ring 4 x 16 KiB, table resident in uniform registers, 8+1 warps x 4 px, 2 blocks/SM"},
     {LV8(4, 2, true, true, 256), "const table, atomic slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(4, 2, false, true, 256), "smem table, atomic slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(4, 2, false, false, 256), "smem table, 128-bit RMW slots, 256 thr x 4 px, 2 blocks/SM"},
@@ -61,19 +61,10 @@ static const LloydVariant LLOYD_VARIANTS[] = {
     {LV8(4, 2, true, false, 256), "const table, RMW slots, 256 thr x 4 px, 2 blocks/SM"},
     {LV8(2, 3, false, false, 256), "smem table, RMW slots, 256 thr x 2 px, 3 blocks/SM"},
     {LVR(2, 4, 2), "TMA ring 4 x 8 KiB, 2 blocks/SM"},
-    {LVR(4, 4, 2), "TMA ring 4 x 16 KiB, 2 blocks/SM"},
+    {LVR(2, 8, 2), "TMA ring 8 x 8 KiB, 2 px per lane and stage, 2 blocks/SM"},
     {LVR(2, 4, 3), "TMA ring 4 x 8 KiB, 3 blocks/SM"},
     {LVR(8, 2, 2), "TMA ring 2 x 32 KiB, 2 blocks/SM"},
-    {LVRF(2, 8, 2, 1), "TMA ring 8 x 8 KiB, no evict-first hint"},
-    {LVRF(2, 8, 2, 2), "TMA ring 8 x 8 KiB, suspend hint"},
-    {LVRF(2, 8, 2, 4), "TMA ring 8 x 8 KiB, L2 prefetch"},
-    {LVRF(2, 8, 2, 6), "TMA ring 8 x 8 KiB, suspend hint + L2 prefetch"},
-    {LVRF(2, 4, 3, 6), "TMA ring 4 x 8 KiB, 3 blocks/SM, suspend hint + L2 prefetch"},
-    {LVRF(2, 8, 2, 8), "TMA ring 8 x 8 KiB, memory side alone (timing experiment, wrong sums)"},
-    {LVRF(2, 8, 2, 16), "TMA ring 8 x 8 KiB, compute side alone (timing experiment, wrong sums)"},
-    {LVRF(2, 4, 2, 8), "TMA ring 4 x 8 KiB, memory side alone (timing experiment, wrong sums)"},
-    {LVRF(2, 8, 2, 32), "TMA ring 8 x 8 KiB, no slot reductions (timing experiment, wrong sums)"},
-    {LVRF(2, 8, 2, 64), "TMA ring 8 x 8 KiB, one slot reduction per pixel (timing experiment, wrong sums)"},
+    {LVRF(2, 8, 2, 8), "TMA ring 8 x 8 KiB, memory side alone (timing experiment, sums dropped)"},
     // k <= 16
     {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},
     {LV16(2, 2, false, true), "smem table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},

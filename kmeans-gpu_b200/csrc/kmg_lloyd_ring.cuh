@@ -42,34 +42,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// Same, but a warp whose phase has not completed is suspended by the hardware for up to `ns`
-// nanoseconds per attempt instead of re-issuing the test (a spinning warp takes issue slots from
-// the warps that still have pixels to work on).
-__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}" ::"r"(bar),
-      "r"(parity), "r"(ns)
-      : "memory");
-}
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
-}
-__device__ __forceinline__ void bulk_g2s_nohint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, UBLKCP).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
@@ -183,34 +159,27 @@ __device__ __forceinline__ void ring_pair_search(const float4& va, const float4&
   ub = __float_as_uint(Vb);
 }
 
-// The exact path for the pixel pair that left the hot loop (cold; every lane of the warp calls it).
-// The hot loop has already added every pixel to the slot its flag sum pointed at (hit_a / hit_b,
-// byte offsets of a cluster): an uncertified pixel is taken out of that slot again and put into the
-// cluster the exact search finds.
+// The exact path for one pixel of the stage that left the hot loop (cold; every lane of the warp
+// calls it).  The hot loop has already added every pixel to the slot its flag sum pointed at (`hit`,
+// the byte offset of a cluster): an uncertified pixel is taken out of that slot again and put into
+// the cluster the exact search finds.
 template <unsigned int SPAN>
-__device__ __noinline__ void ring_slow_pair(const CentRec* __restrict__ g_tab, unsigned int k, uint32_t pair_addr,
-                                            unsigned int need, uint32_t hit_a, uint32_t hit_b, float lmax, float cmax,
-                                            uint32_t slot_tid_u32, unsigned int cluster_stride, unsigned int& slow) {
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool nd = (need >> i) & 1u;
-    if (!__any_sync(0xffffffffu, nd)) continue;
-    const float4 v = lds128(pair_addr + i * 512);
-    const float eps = fast::score_eps(v.x, v.w, lmax, cmax);
-    const unsigned int idx = warp_exact_argmin<true>(g_tab, k, nd, v.x, v.y, v.z, v.w, eps, 0u);
-    if (nd) {
-      slot_add<SPAN, -1>(slot_tid_u32 | (i ? hit_b : hit_a), v.x, v.y, v.z);
-      slot_add<SPAN, 1>(slot_tid_u32 + idx * cluster_stride, v.x, v.y, v.z);
-      ++slow;
-    }
+__device__ __noinline__ void ring_slow_pixel(const CentRec* __restrict__ g_tab, unsigned int k, uint32_t px_addr, bool nd,
+                                             uint32_t hit, float lmax, float cmax, uint32_t slot_tid_u32,
+                                             unsigned int cluster_stride, unsigned int& slow) {
+  if (!__any_sync(0xffffffffu, nd)) return;
+  const float4 v = lds128(px_addr);
+  const float eps = fast::score_eps(v.x, v.w, lmax, cmax);
+  const unsigned int idx = warp_exact_argmin<true>(g_tab, k, nd, v.x, v.y, v.z, v.w, eps, 0u);
+  if (nd) {
+    slot_add<SPAN, -1>(slot_tid_u32 | hit, v.x, v.y, v.z);
+    slot_add<SPAN, 1>(slot_tid_u32 + idx * cluster_stride, v.x, v.y, v.z);
+    ++slow;
   }
 }
 
-// FLAGS (experiments): 1 = no L2 evict-first hint on the copies, 2 = suspend-time hint on the waits,
-// 4 = the producer prefetches the tile 2 D stages ahead into L2,
-// 8 = memory side alone (consumers wait, touch the stage and release it: wrong sums, timing only),
-// 16 = compute side alone (only the first D tiles are ever copied, nobody waits: wrong sums, timing only),
-// 32 = no slot reductions, 64 = one slot reduction per pixel (wrong sums, timing only)
+// FLAGS: 8 = timing experiment, the memory side alone (consumers wait, touch the stage and release
+// it; the sums are dropped and the centroids kept)
 template <int KT, int CWARPS, int P, int D, int MINB, int FLAGS = 0>
 __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     k_lloyd_ring(JobPtrs J, const float4* __restrict__ work, unsigned long long n, int color_space, int distributed_mode,
@@ -218,7 +187,6 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
   static_assert(KT == 8, "the uniform-register table holds 8 centroids");
   static_assert(P == 2 || P == 4 || P == 8, "whole packed pixel pairs per lane and stage");
   using L = RingLayout<KT, CWARPS, P, D>;
-  constexpr unsigned int PAIRS = P / 2;  // pairs per lane and stage
   constexpr unsigned int THREADS = L::THREADS, CTHREADS = L::CTHREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ bool s_last;
@@ -263,21 +231,12 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     const uint64_t policy = l2_evict_first_policy();
     const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(work) + (unsigned long long)blockIdx.x * (BT * 16);
     const unsigned long long gstep = (unsigned long long)gridDim.x * (BT * 16);
-    for (unsigned int t = 0; t < ((FLAGS & 16) ? min(my_tiles, (unsigned int)D) : my_tiles); ++t) {
+    for (unsigned int t = 0; t < my_tiles; ++t) {
       const unsigned int s = t & (D - 1);
-      if (t >= D) {
-        if (FLAGS & 2)
-          mbar_wait_suspend(empty_u32 + s * 8, ((t / D) - 1u) & 1u, 1000u);
-        else
-          mbar_wait(empty_u32 + s * 8, ((t / D) - 1u) & 1u);
-      }
+      if (t >= D) mbar_wait(empty_u32 + s * 8, ((t / D) - 1u) & 1u);
       if (lane == 0) {
         mbar_expect_tx(full_u32 + s * 8, L::STAGE_BYTES);
-        if (FLAGS & 1)
-          bulk_g2s_nohint(ring_u32 + s * L::STAGE_BYTES, gsrc, L::STAGE_BYTES, full_u32 + s * 8);
-        else
-          bulk_g2s(ring_u32 + s * L::STAGE_BYTES, gsrc, L::STAGE_BYTES, full_u32 + s * 8, policy);
-        if ((FLAGS & 4) && t + 2 * D < my_tiles) bulk_prefetch_l2(gsrc + 2 * D * gstep, L::STAGE_BYTES);
+        bulk_g2s(ring_u32 + s * L::STAGE_BYTES, gsrc, L::STAGE_BYTES, full_u32 + s * 8, policy);
       }
       gsrc += gstep;
     }
@@ -339,64 +298,58 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
     constexpr unsigned int FLUSH_PX = 480;
     using RC = RingCert<KT, CTHREADS * 4>;  // slot stride of a cluster in bytes
     constexpr unsigned int IDX_MASK = RC::IDX_MASK, CERT_MASK = RC::CERT_MASK, CERT_ONE = RC::CERT_ONE;
-    const unsigned int my_pairs = my_tiles * PAIRS;
 
-    unsigned int u = 0;  // pixel pairs of this lane done so far; tile = u / PAIRS
-    while (u < my_pairs) {
-      const unsigned int u_stop = min(my_pairs, u + (FLUSH_PX - since_flush) / 2);
-      const unsigned int u_begin = u;
-      unsigned int need = 0, hit_a = 0, hit_b = 0;
-      // ---- hot loop: one pixel pair per lane and iteration, no calls, table resident --------------
-      for (; u < u_stop; ++u) {
-        const unsigned int t = u / PAIRS, sub = u % PAIRS;
+    unsigned int t = 0;  // stages (tiles) of this block done so far by this warp
+    while (t < my_tiles) {
+      const unsigned int t_stop = min(my_tiles, t + (FLUSH_PX - since_flush) / P);
+      const unsigned int t_begin = t;
+      unsigned int need = 0, hit[P];
+      // ---- hot loop: one stage (P / 2 pixel pairs per lane) per iteration, no calls, table resident ----
+      for (; t < t_stop; ++t) {
         const unsigned int s = t & (D - 1);
-        if (sub == 0 && (!(FLAGS & 16) || t < D)) {
-          if (FLAGS & 2)
-            mbar_wait_suspend(full_u32 + s * 8, (t / D) & 1u, 1000u);
-          else
-            mbar_wait(full_u32 + s * 8, (t / D) & 1u);
-        }
-        const uint32_t pair_addr = ring_lane_u32 + s * L::STAGE_BYTES + sub * 1024;
-        const float4 va = lds128(pair_addr), vb = lds128(pair_addr + 512);
-        if (FLAGS & 8) {
-          if (va.x + vb.x == 12345.678f) slow++;
-          if (sub == PAIRS - 1 && lane == 0) mbar_arrive(empty_u32 + s * 8);
+        mbar_wait(full_u32 + s * 8, (t / D) & 1u);
+        const uint32_t stage_addr = ring_lane_u32 + s * L::STAGE_BYTES;
+        float4 v[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = lds128(stage_addr + i * 512);
+        if (FLAGS & 8) {  // timing experiment: the memory side alone
+          if (v[0].x + v[P - 1].x == 12345.678f) slow++;
+          if (lane == 0) mbar_arrive(empty_u32 + s * 8);
           continue;
         }
-        unsigned int ua, ub;
-        ring_pair_search<KT, CTHREADS * 4>(va, vb, tq, lmax_u, cmax_v, ua, ub);
-        const bool cert_a = (ua & CERT_MASK) == CERT_ONE, cert_b = (ub & CERT_MASK) == CERT_ONE;
-        // every pixel goes to the slot its flag sum points at; the rare uncertified one is moved by
-        // the exact path below (no predicate, no branch around the reductions)
-        if (FLAGS & 32) {  // timing experiment: no accumulation at all (wrong sums)
-          if ((ua ^ ub) == 0x12345u) slow++;
-        } else if (FLAGS & 64) {  // timing experiment: one reduction per pixel instead of four (wrong sums)
-          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((ua & IDX_MASK) | slot_tid_u32), "r"(__float_as_uint(va.x)) : "memory");
-          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((ub & IDX_MASK) | slot_tid_u32), "r"(__float_as_uint(vb.x)) : "memory");
-        } else {
-        slot_add<L::SLOT_SPAN>((ua & IDX_MASK) | slot_tid_u32, va.x, va.y, va.z);
-        slot_add<L::SLOT_SPAN>((ub & IDX_MASK) | slot_tid_u32, vb.x, vb.y, vb.z);
+        bool all_cert = true;
+#pragma unroll
+        for (int h = 0; h < P / 2; ++h) {
+          unsigned int ua, ub;
+          ring_pair_search<KT, CTHREADS * 4>(v[2 * h], v[2 * h + 1], tq, lmax_u, cmax_v, ua, ub);
+          // every pixel goes to the slot its flag sum points at; the rare uncertified one is moved by
+          // the exact path below (no predicate, no branch around the reductions)
+          slot_add<L::SLOT_SPAN>((ua & IDX_MASK) | slot_tid_u32, v[2 * h].x, v[2 * h].y, v[2 * h].z);
+          slot_add<L::SLOT_SPAN>((ub & IDX_MASK) | slot_tid_u32, v[2 * h + 1].x, v[2 * h + 1].y, v[2 * h + 1].z);
+          all_cert &= (ua & CERT_MASK) == CERT_ONE && (ub & CERT_MASK) == CERT_ONE;
+          hit[2 * h] = ua;
+          hit[2 * h + 1] = ub;
         }
-        if (__any_sync(0xffffffffu, !(cert_a && cert_b))) {
-          need = (cert_a ? 0u : 1u) | (cert_b ? 0u : 2u);
-          hit_a = ua;
-          hit_b = ub;
+        if (__any_sync(0xffffffffu, !all_cert)) {
+#pragma unroll
+          for (int i = 0; i < P; ++i) need |= ((hit[i] & CERT_MASK) == CERT_ONE ? 0u : 1u) << i;
           break;
         }
-        if (sub == PAIRS - 1 && lane == 0 && !(FLAGS & 16)) mbar_arrive(empty_u32 + s * 8);  // stage consumed by this warp
+        if (lane == 0) mbar_arrive(empty_u32 + s * 8);  // stage consumed by this warp
       }
-      // ---- cold: exact path of the pair that left the loop, slot flush ------------------------------
-      if (u < u_stop) {
-        const unsigned int t = u / PAIRS, sub = u % PAIRS;
+      // ---- cold: exact path of the stage that left the loop, slot flush ------------------------------
+      if (t < t_stop) {
         const unsigned int s = t & (D - 1);
-        ring_slow_pair<L::SLOT_SPAN>(J.tab, k, ring_lane_u32 + s * L::STAGE_BYTES + sub * 1024, need, hit_a & IDX_MASK, hit_b & IDX_MASK, lmax,
-                                     cmax, slot_tid_u32, CTHREADS * 4, slow);
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+          ring_slow_pixel<L::SLOT_SPAN>(J.tab, k, ring_lane_u32 + s * L::STAGE_BYTES + i * 512, (need >> i) & 1u,
+                                        hit[i] & IDX_MASK, lmax, cmax, slot_tid_u32, CTHREADS * 4, slow);
         __syncwarp();
-        if (sub == PAIRS - 1 && lane == 0) mbar_arrive(empty_u32 + s * 8);
-        ++u;
+        if (lane == 0) mbar_arrive(empty_u32 + s * 8);
+        ++t;
       }
-      since_flush += 2 * (u - u_begin);
-      if (since_flush + 2 > FLUSH_PX) flush();
+      since_flush += P * (t - t_begin);
+      if (since_flush + P > FLUSH_PX) flush();
     }
 
     // ragged tail (< CTHREADS * P pixels): the block whose turn it would be, straight from global
@@ -422,7 +375,7 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (FLAGS & (8 | 16 | 32 | 64)) {
+    if (FLAGS & 8) {
       // timing experiments produce wrong sums: drop them, keep the centroids, count the pass
       for (unsigned int c = tid; c < J.acc_copies * k * 4; c += THREADS) J.acc[c] = 0;
       if (tid == 0) {
