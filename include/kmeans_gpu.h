@@ -179,6 +179,13 @@ int kmg_job_run(kmg_job* job, uint32_t* passes_out, void* stream);
 int kmg_job_stats(kmg_job* job, uint32_t* converged_out, uint32_t* passes_out, uint64_t* slow_pixels_out,
                   void* stream);
 
+/* Work done by the lazy farthest-point rounds of the last kmg_job_init (kmg_init_lazy.cuh): sweeps over
+ * the 2 B/px bound array (one per lazy round if every round resolved at once), pixels refreshed,
+ * (pixel, centroid) pairs folded into a running minimum, and how many of those pairs needed the exact
+ * distance — full sweeps would fold (k - 1) * w * h pairs, all of them exactly. */
+int kmg_job_init_stats(kmg_job* job, uint32_t* sweeps_out, uint64_t* refreshed_out, uint64_t* pairs_out,
+                       uint64_t* exact_out, void* stream);
+
 /* Reduced integer sums of the last pass: k x {sum0, sum1, sum2, count}, sums in units of 2^-15
  * (the k x 4 accumulators the multi-GPU path all-reduces; sums of shards add up exactly). */
 int kmg_job_get_sums(kmg_job* job, int64_t* sums_out, void* stream);

@@ -13,6 +13,7 @@ const HEADERS: &[&str] = &[
     "kmg_kernels.cuh",
     "kmg_lloyd_ring.cuh",
     "kmg_audit.cuh",
+    "kmg_init_lazy.cuh",
     "kmg_small.cuh",
     "kmg_math.cuh",
 ];

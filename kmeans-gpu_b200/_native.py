@@ -77,6 +77,7 @@ SIGNATURES = {
     "kmg_job_step": (C.c_int, [_vp, C.c_uint32, _vp]),
     "kmg_job_run": (C.c_int, [_vp, _u32p, _vp]),
     "kmg_job_stats": (C.c_int, [_vp, _u32p, _u32p, _u64p, _vp]),
+    "kmg_job_init_stats": (C.c_int, [_vp, _u32p, _u64p, _u64p, _u64p, _vp]),
     "kmg_job_get_sums": (C.c_int, [_vp, C.POINTER(C.c_int64), _vp]),
     "kmg_comm_unique_id": (C.c_int, [_vp, _u8p]),
     "kmg_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),

@@ -43,6 +43,14 @@ struct JobState {
   unsigned int pad0;
   unsigned long long slow_pixels;
   unsigned long long pad1;
+  // lazy farthest-point initialisation (kmg_init_lazy.cuh)
+  unsigned int init_tau16;       // candidates of the next sweep: pixels whose 16-bit upper bound is >= this
+  unsigned int init_ncmax;       // 1 + the largest 16-bit bound among the pixels the sweep skipped (0: none skipped)
+  unsigned int init_done_round;  // last round resolved
+  unsigned int init_attempts;    // sweeps so far (statistics)
+  unsigned long long init_refreshed;  // pixel refreshes so far (statistics)
+  unsigned long long init_folds;      // (pixel, centroid) pairs folded so far (statistics)
+  unsigned long long init_exact;      // of those, pairs that needed the exact distance (statistics)
 };
 
 struct JobPtrs {
@@ -645,6 +653,13 @@ __global__ void k_init_seed(JobPtrs J, const float4* __restrict__ work, unsigned
       J.cent[0] = make_float4(v.x, v.y, v.z, 1.0f);
     }
     for (unsigned int i = 0; i < J.st->k; ++i) J.keys[i] = 0ull;
+    J.st->init_tau16 = 0;
+    J.st->init_ncmax = 0;
+    J.st->init_done_round = 0;
+    J.st->init_attempts = 0;
+    J.st->init_refreshed = 0ull;
+    J.st->init_folds = 0ull;
+    J.st->init_exact = 0ull;
   }
 }
 
@@ -657,10 +672,13 @@ __global__ void k_init_seed(JobPtrs J, const float4* __restrict__ work, unsigned
 //   colour broadcast of the round happen inside the round's own launch (no NCCL, no extra launch).
 //   Parity (k - j) & 1 alternates down to the first Lloyd pass (parity 0); flags carry
 //   seq_base - j, disjoint from the passes' seq_base + pass + 1.
+// ub (may be NULL): the 16-bit upper bounds of the running minima, kept up to date for the lazy
+// rounds that follow (kmg_init_lazy.cuh).
 template <bool FIRST, int PICK>
 __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __restrict__ work,
                                                     float* __restrict__ dmin, unsigned long long n,
-                                                    unsigned long long pixel_offset, unsigned int j, PeerXchg X) {
+                                                    unsigned long long pixel_offset, unsigned int j, PeerXchg X,
+                                                    unsigned short* __restrict__ ub = nullptr) {
   __shared__ unsigned long long s_key[8];
   __shared__ bool s_last;
   // centroid j-1 was resolved into J.cent[j-1] by the previous round (or k_init_seed for j == 1).
@@ -692,6 +710,7 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
         // sectors of the plane stay clean in HBM.
         const float dm = fminf(old[i], d);
         if (FIRST || d < old[i]) dmin[p] = dm;
+        if (ub && (FIRST || d < old[i])) ub[p] = (unsigned short)((__float_as_uint(dm) + 0xffffu) >> 16);
         const unsigned long long key =
             ((unsigned long long)__float_as_uint(dm) << 32) | (((pixel_offset + p) & 0xffffffffull) ^ 15ull);
         best = key > best ? key : best;
@@ -790,6 +809,10 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
     J.cent[j] = col;
     J.keys[j] = key;
     J.st->ticket = 0;
+    if (ub) {  // threshold of the first lazy round: farthest-point distances never grow
+      J.st->init_tau16 = __float_as_uint(__uint_as_float((unsigned int)(key >> 32)) * 0.98f) >> 16;
+      J.st->init_done_round = j;
+    }
   }
 }
 

@@ -167,6 +167,13 @@ class Job:
                                                    _stream_ptr(stream)))
         return {"converged": conv.value, "passes": passes.value, "slow_pixels": slow.value}
 
+    def init_stats(self, stream=None):
+        """Work of the lazy farthest-point rounds: sweeps, refreshed pixels, exact distances evaluated."""
+        sw, re, fo, ex = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _native.check(self.proc._lib.kmg_job_init_stats(self._job, C.byref(sw), C.byref(re), C.byref(fo), C.byref(ex),
+                                                        _stream_ptr(stream)))
+        return {"sweeps": sw.value, "refreshed": re.value, "pairs": fo.value, "exact": ex.value}
+
     def sums(self, stream=None) -> np.ndarray:
         """k x (sum0, sum1, sum2, count) of the last pass, sums in units of 2^-15."""
         acc = np.zeros((self.k, 4), np.int64)

@@ -807,3 +807,59 @@ def test_certificate_audit_rgb_colour_space(proc, D, K, torch):
                 if search != 3:
                     for mode in (1, 2):
                         assert D.audit(proc, cent, search, mode, rgba=img, w=4096, h=4096, color_space=K.ColorSpace.Rgb)[0] == 0
+
+
+# ---- lazy farthest-point rounds (kmg_init_lazy.cuh) against the one-sweep-per-round kernels -----------
+
+@pytest.mark.parametrize("side,k,blobs,eager_rounds", [(1024, 64, 128, 8), (1536, 256, 512, 8), (700, 33, 0, 1), (512, 300, 4, 3),
+                                                       (640, 12, 24, 2)])
+def test_lazy_init_matches_full_sweeps(K, D, oracle, torch, monkeypatch, side, k, blobs, eager_rounds):
+    """Same picks, same max-min distances (bit for bit), same centroids: the lazy rounds only skip
+    pixels that provably cannot win.  blobs=4 with k=300: far more clusters than colours groups, the
+    distances collapse and the threshold has to chase them down."""
+    img = oracle.synth(side * side, seed=11, blobs=blobs).reshape(side, side, 4)
+    res = []
+    monkeypatch.setenv("KMG_INIT_LAZY_MIN_K", "0")
+    monkeypatch.setenv("KMG_INIT_EAGER_ROUNDS", str(eager_rounds))
+    for eager in ("1", "0"):
+        monkeypatch.setenv("KMG_INIT_EAGER", eager)
+        p = K.ImageProcessor(0)
+        try:
+            work = D.convert(p, dev_rgba(torch, img))
+            job = D.Job(p, work, side, side, k, opts=K.Opts(max_dim=0))
+            idx, dist = job.init()
+            st = job.init_stats()
+            res.append((idx.copy(), dist.copy(), job.centroids().copy(), st))
+            job.close()
+        finally:
+            p.close()
+    (i0, d0, c0, _), (i1, d1, c1, st) = res
+    assert i0.tolist() == i1.tolist()
+    assert np.array_equal(bits(d0), bits(d1)) and np.array_equal(bits(c0), bits(c1))
+    assert st["sweeps"] >= k - 1 - eager_rounds and st["exact"] <= st["pairs"], st
+    if k >= 64:
+        assert st["refreshed"] < 0.25 * (k - 1 - eager_rounds) * side * side, st  # full sweeps would refresh every pixel every round
+
+
+def test_lazy_init_flat_image_and_zero_maximum(K, D, oracle, torch, monkeypatch):
+    """Two colours, k = 6: from round 3 on every distance is zero — the threshold must fall to 'every
+    pixel' and the zero maximum must select pixel 0 (plus_plus_init.wgsl: Candidate(0, 0.0))."""
+    w, h = 300, 200
+    img = np.zeros((h, w, 4), np.uint8)
+    img[..., 3] = 255
+    img[:, : w // 3, 0] = 200
+    monkeypatch.setenv("KMG_INIT_LAZY_MIN_K", "0")
+    monkeypatch.setenv("KMG_INIT_EAGER_ROUNDS", "1")
+    proc = K.ImageProcessor(0)
+    try:
+        work = D.convert(proc, dev_rgba(torch, img))
+        job = D.Job(proc, work, w, h, 6, opts=K.Opts(max_dim=0))
+        idx, dist = job.init()
+        assert job.init_stats()["sweeps"] >= 4
+        lab = oracle.convert(img)
+        ocent, oidx, odist = oracle.init(lab, w, h, 6, int(w * 0.5625), int(h * 0.93359375))
+        assert idx.tolist() == oidx.tolist() and np.array_equal(bits(dist), bits(odist))
+        assert np.array_equal(bits(job.centroids()), bits(ocent))
+        job.close()
+    finally:
+        proc.close()
