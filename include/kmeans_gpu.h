@@ -202,7 +202,12 @@ int kmg_comm_destroy(kmg_ctx* ctx);
  * kmg_comm_init when CUDA IPC peer mapping works between all ranks; at most 8 ranks). */
 int kmg_comm_mode(kmg_ctx* ctx);
 /* Marks the job as one shard of a distributed problem: global_w/global_h describe the whole image
- * and row_offset the first row of this shard (used by the init seed and tie rule). */
+ * and row_offset the first row of this shard (used by the init seed and tie rule).
+ * One live sharded job per context (KMG_ERR_BAD_ARG otherwise): the peer mailboxes of mode 2 are per
+ * context.  kmg_job_step is asynchronous, but the ranks of a sharded job must launch matching passes
+ * within 4 s of each other: a rank that waits longer gives up and poisons the mailboxes, every rank of
+ * the job then fails with KMG_ERR_NCCL at its next state read (kmg_job_run / kmg_job_stats / ...), and
+ * the communicator has to be re-created (kmg_comm_destroy + kmg_comm_init). */
 int kmg_job_set_shard(kmg_job* job, uint32_t global_w, uint32_t global_h, uint32_t row_offset);
 
 /* Fused remap on device buffers (mode as kmg_reduce_mode).  centroids_host: k x 4 floats. */
@@ -235,6 +240,10 @@ int kmg_dev_fp32_peak(kmg_ctx* ctx, double* fma_per_second_out);
  * bound) and in *uncertified_out the pixels production would hand to its exact path.
  *   search  0: 8-entry table, all scores kept   1: 16-entry table   2: chunked search, any k
  *           3: the resident-table search of the k <= 8 Lloyd pass (kmg_lloyd_ring.cuh)
+ *           4: margin probe — *wrong_out = pixels whose fast arg-min differs from the reference label (the
+ *              certificate has to catch every one of them), *uncertified_out = the largest
+ *              (fast score gap between the two labels) / eps among them, in millionths: how much of the
+ *              error bound is ever used
  *   mode    0: Lloyd pass / assignment — d_work is the exact work plane of the w*h pixels
  *           1: remap, replace   2: remap, ordered dither — d_rgba is the RGBA8 image (fast Lab in the
  *              kernel; the reference label is the scan of the exact pixel + dither offset) */

@@ -247,6 +247,7 @@ struct kmg_ctx {
   void* mbox_own = nullptr;                // this GPU's mailbox (cudaMalloc, exported through CUDA IPC)
   void* mbox_peer[MAX_PEERS] = {nullptr};  // every rank's mailbox as mapped here (own entry = mbox_own)
   uint32_t xchg_seq = 0x1234567u;          // flag sequence base handed to the next sharded job
+  std::atomic<int> live_sharded{0};        // sharded jobs alive on this context (at most one)
   // constant-bank table slots (kmg_kernels.cuh: c_tab), handed to jobs with k <= 8
   void* c_tab_dev = nullptr;
   bool big_block_acc = true;   // KMG_LLOYDG_BLOCKACC=0: accumulate through L2 atomics instead of shared memory
@@ -895,7 +896,9 @@ static int job_read_state(kmg_job* j, cudaStream_t s) {
   CU(cudaMemcpyAsync(j->h_state, j->P.st, sizeof(JobState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (j->h_state->conv == PASS_FAULT)
-    return fail(KMG_ERR_NCCL, "a peer GPU did not deliver its partial sums within 4 s (pass %u)", j->h_state->passes);
+    return fail(KMG_ERR_NCCL, "a peer GPU did not deliver its partial sums within 4 s, or had given up before (pass %u); "
+                              "every rank of the job fails together and the communicator stays unusable until it is re-created",
+                j->h_state->passes);
   return KMG_OK;
 }
 
@@ -1091,6 +1094,7 @@ extern "C" int kmg_job_create(kmg_ctx* ctx, const float* d_work, uint32_t w, uin
 extern "C" void kmg_job_destroy(kmg_job* j) {
   if (!j) return;
   cudaSetDevice(j->ctx->device);
+  if (j->sharded) j->ctx->live_sharded.store(0);
   if (j->owns_blob && j->blob) cudaFree(j->blob);
   if (j->owns_dmin && j->dmin) cudaFree(j->dmin);
   if (j->owns_h_state && j->h_state) cudaFreeHost(j->h_state);
@@ -1102,6 +1106,15 @@ extern "C" int kmg_job_set_shard(kmg_job* j, uint32_t gw, uint32_t gh, uint32_t 
   if (gw != j->w || (unsigned long long)row_offset + j->h > gh)
     return fail(KMG_ERR_BAD_ARG, "shard rows [%u,%u) of width %u do not fit the %ux%u image", row_offset,
                 row_offset + j->h, j->w, gw, gh);
+  // One live sharded job per context: the mailboxes of the in-kernel exchange are indexed by
+  // (pass parity, rank) only, so two sharded jobs stepping on different streams of one context would
+  // overwrite each other's partial sums.  Destroy the previous job (or use a second kmg_ctx).
+  if (!j->sharded) {
+    int expected = 0;
+    if (!j->ctx->live_sharded.compare_exchange_strong(expected, 1))
+      return fail(KMG_ERR_BAD_ARG, "kmg_job_set_shard: this context already has a live sharded job (one at a time; "
+                                   "destroy it first or use another kmg_ctx)");
+  }
   j->sharded = true;
   // every rank creates its sharded jobs in the same order, so the bases agree across ranks
   j->xchg_base = j->ctx->xchg_seq;
@@ -1268,7 +1281,7 @@ extern "C" int kmg_dev_audit(kmg_ctx* ctx, const float* d_work, const uint8_t* d
                              const float* cent, uint32_t k, int cs, int search, int mode, uint64_t* wrong_out,
                              uint64_t* uncertified_out, void* stream) {
   if (!ctx || !cent || !wrong_out) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: NULL argument");
-  if (mode < 0 || mode > 2 || search < 0 || search > 3) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: unknown search %d / mode %d", search, mode);
+  if (mode < 0 || mode > 2 || search < 0 || search > 4) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: unknown search %d / mode %d", search, mode);
   if (mode == 0 ? !d_work : !d_rgba) return fail(KMG_ERR_BAD_ARG, "kmg_dev_audit: mode %d needs the %s", mode, mode == 0 ? "work plane" : "RGBA8 image");
   TRY(validate_dims(w, h, k));
   if (((search == 0 || search == 3) && k > 8) || (search == 1 && k > 16))
@@ -1288,7 +1301,24 @@ extern "C" int kmg_dev_audit(kmg_ctx* ctx, const float* d_work, const uint8_t* d
   unsigned long long* dc = (unsigned long long*)counters.p;
   const float4* work = (const float4*)d_work;
   const uint32_t* rgba = (const uint32_t*)d_rgba;
-  int r = search == 0   ? launch_audit<0>(&t.job, work, rgba, w, n, mode, dc, s)
+  if (search == 4) {  // margin probe
+    const size_t smem = tab_smem_bytes(pad32(k));
+    const int grid = ctx->sms * (smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4));
+    if (mode == 0) {
+      CU(cudaFuncSetAttribute(k_audit_margin<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_audit_margin<0><<<grid, 256, smem, s>>>(t.job.P, work, rgba, w, n, cs, ctx->d_lut, dc);
+    } else if (mode == 1) {
+      CU(cudaFuncSetAttribute(k_audit_margin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_audit_margin<1><<<grid, 256, smem, s>>>(t.job.P, work, rgba, w, n, cs, ctx->d_lut, dc);
+    } else {
+      CU(cudaFuncSetAttribute(k_audit_margin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_audit_margin<2><<<grid, 256, smem, s>>>(t.job.P, work, rgba, w, n, cs, ctx->d_lut, dc);
+    }
+    LAUNCHED(ctx);
+    CHECK_LAUNCH();
+  }
+  int r = search == 4   ? KMG_OK
+          : search == 0 ? launch_audit<0>(&t.job, work, rgba, w, n, mode, dc, s)
           : search == 1 ? launch_audit<1>(&t.job, work, rgba, w, n, mode, dc, s)
           : search == 2 ? launch_audit<2>(&t.job, work, rgba, w, n, mode, dc, s)
                         : launch_audit<3>(&t.job, work, rgba, w, n, mode, dc, s);

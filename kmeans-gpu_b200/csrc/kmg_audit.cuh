@@ -121,4 +121,73 @@ __global__ void __launch_bounds__(256) k_audit(JobPtrs J, const float4* __restri
   }
 }
 
+// Margin probe: how much of the error bound is ever used?  Every pixel evaluates the fast score of
+// all k centroids (the production arithmetic: pix_coef + score1, on the exact plane or on the fast
+// pixel of the remap kernels) and the reference scan.  Where the fast arg-min is NOT the reference
+// label the production code relies on the certificate to notice: the gap between the fast scores of
+// the two labels must be below eps.  counters[0] = such pixels, counters[1] = the largest gap / eps
+// seen among them, in millionths (1e6 = the bound was exactly used up; every value below leaves room).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_audit_margin(JobPtrs J, const float4* __restrict__ work,
+                                                      const uint32_t* __restrict__ rgba, unsigned int w, unsigned long long n,
+                                                      int color_space, const float* __restrict__ lut_g,
+                                                      unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CentRec* s_tab = reinterpret_cast<CentRec*>(smem_raw);
+  __shared__ float lut[256];
+  const unsigned int tid = threadIdx.x;
+  const unsigned int k = J.st->k;
+  const unsigned int kp = pad32(k);
+  tab_to_smem(s_tab, J.tab, kp, tid, 256);
+  lut[tid] = lut_g[tid];
+  const float lmax = J.st->lmax, cmax = J.st->cmax, thr = J.st->dither_threshold;
+  __syncthreads();
+  constexpr bool CONV = MODE != 0;
+  const float conv_k = color_space == 0 ? fast::LAB_ERR : fast::RGB_ERR;
+  unsigned long long differ = 0, worst = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+  for (unsigned long long p = (unsigned long long)blockIdx.x * 256 + tid; p < n; p += stride) {
+    float L, a, b, C;
+    float4 e;
+    if (MODE == 0) {
+      e = work[p];
+      L = e.x; a = e.y; b = e.z; C = e.w;
+    } else {
+      const uint32_t v = rgba[p];
+      float off;
+      remap_fast_pixel<(MODE == 2 ? 1 : 0)>(v, lut, color_space, thr, (unsigned int)(p % w), (unsigned int)(p / w), L, a, b, C, off);
+      e = remap_exact_pixel<(MODE == 2 ? 1 : 0)>(v, lut, color_space, off);
+    }
+    const unsigned int want = reference_scan(J.cent, k, e.x, e.y, e.z, e.w);
+    const fast::PixCoef pc = fast::pix_coef(L, a, b, C);
+    float m = 3.0e38f, s_want = 0.0f;
+    unsigned int im = 0;
+    for (unsigned int j = 0; j < k; ++j) {
+      const float sc = score1(pc, rec_at(s_tab, j)->q);
+      if (sc < m) {
+        m = sc;
+        im = j;
+      }
+      if (j == want) s_want = sc;
+    }
+    if (im != want) {
+      // masked duplicates never win the fast search; the reference label is then the lowest index of
+      // the duplicate group and scores the same as its twin
+      const float eps = total_eps<CONV>(fast::score_eps(L, C, lmax, cmax), m, conv_k, L, C, pc.p1, pc.hs, cmax);
+      const float ratio = (s_want - m) / eps;
+      if (s_want < 1.0e29f) {
+        ++differ;
+        const unsigned long long r = (unsigned long long)(fminf(fmaxf(ratio, 0.0f), 1.0e6f) * 1.0e6f);
+        worst = r > worst ? r : worst;
+      }
+    }
+  }
+  differ = (unsigned long long)warp_sum_i64((long long)differ);
+  worst = warp_max_u64(worst);
+  if ((tid & 31) == 0) {
+    if (differ) atomicAdd(counters, differ);
+    if (worst) atomicMax(counters + 1, worst);
+  }
+}
+
 }  // namespace kmg

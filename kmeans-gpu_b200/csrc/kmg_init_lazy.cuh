@@ -59,21 +59,7 @@ __device__ __forceinline__ bool init_exchange(const PeerXchg& X, unsigned int k,
     __threadfence_system();
   }
   __syncthreads();
-  if (threadIdx.x < X.n_ranks) {
-    volatile unsigned int* theirs = X.flags[threadIdx.x] + par * MAX_PEERS + X.rank;
-    *theirs = seq;
-    volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + threadIdx.x;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (*mine != seq) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 4000000000ull) {  // 4 s: a peer never reached this round
-        *s_fault = 1;
-        break;
-      }
-    }
-    __threadfence_system();
-  }
+  if (threadIdx.x < X.n_ranks) xchg_flags(X, par, seq, threadIdx.x, s_fault);
   __syncthreads();
   if (*s_fault) return false;
   if (threadIdx.x == 0) {

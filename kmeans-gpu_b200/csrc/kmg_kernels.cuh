@@ -81,6 +81,41 @@ struct PeerXchg {
   unsigned int* flags[MAX_PEERS];
 };
 constexpr unsigned int PASS_FAULT = 0xffffffffu;  // JobState::conv when a peer did not answer
+constexpr unsigned int XCHG_POISON = 0xdeadbeefu; // flag value a rank that gave up leaves in every mailbox
+
+// Flag half of a mailbox exchange; threads 0 .. n_ranks-1 of the block call it after the data has
+// been stored to the peers and fenced.  Thread r raises this rank's flag in peer r's mailbox and waits
+// for peer r's flag in its own.  A rank that waits longer than 4 s (a peer never launched the
+// matching kernel) gives up — and poisons its flag in EVERY mailbox, both parities, so that the peers
+// fault in their current or next exchange as well instead of finishing the pass and running on with
+// centroids this rank never got: all ranks of a job fail together (KMG_ERR_NCCL on each), and the
+// communicator stays poisoned until kmg_comm_destroy / kmg_comm_init.
+__device__ __forceinline__ void xchg_flags(const PeerXchg& X, unsigned int par, unsigned int seq, unsigned int r,
+                                           unsigned int* s_fault) {
+  volatile unsigned int* theirs = X.flags[r] + par * MAX_PEERS + X.rank;
+  if (*theirs != XCHG_POISON) *theirs = seq;
+  volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + r;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    const unsigned int v = *mine;
+    if (v == seq) break;
+    bool fault = v == XCHG_POISON;
+    if (!fault) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      fault = t1 - t0 > 4000000000ull;
+    }
+    if (fault) {
+      *s_fault = 1;
+      for (unsigned int q = 0; q < X.n_ranks; ++q) {
+        *(volatile unsigned int*)(X.flags[q] + X.rank) = XCHG_POISON;
+        *(volatile unsigned int*)(X.flags[q] + MAX_PEERS + X.rank) = XCHG_POISON;
+      }
+      break;
+    }
+  }
+  __threadfence_system();
+}
 
 // The job blob of frame f in a batch: every pointer shifted by f * blob_stride bytes.
 __device__ __forceinline__ JobPtrs job_at(JobPtrs J, size_t off) {
@@ -763,21 +798,7 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
       __threadfence_system();
     }
     __syncthreads();
-    if (threadIdx.x < X.n_ranks) {
-      volatile unsigned int* theirs = X.flags[threadIdx.x] + par * MAX_PEERS + X.rank;
-      *theirs = seq;
-      volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + threadIdx.x;
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (*mine != seq) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) {  // 4 s: a peer never launched this round
-          s_fault = 1;
-          break;
-        }
-      }
-      __threadfence_system();
-    }
+    if (threadIdx.x < X.n_ranks) xchg_flags(X, par, seq, threadIdx.x, &s_fault);
     __syncthreads();
     if (threadIdx.x == 0) {
       if (s_fault) {
@@ -876,21 +897,7 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, int mode, const
     }
     __threadfence_system();
     __syncthreads();
-    if (tid < X.n_ranks) {
-      volatile unsigned int* theirs = X.flags[tid] + par * MAX_PEERS + X.rank;
-      *theirs = seq;
-      volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + tid;
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (*mine != seq) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) {  // 4 s: a peer never launched this pass
-          s_fault = 1;
-          break;
-        }
-      }
-      __threadfence_system();
-    }
+    if (tid < X.n_ranks) xchg_flags(X, par, seq, tid, &s_fault);
     __syncthreads();
     if (s_fault) {
       if (tid == 0) {
