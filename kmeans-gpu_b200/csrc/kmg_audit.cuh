@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(256) k_audit(JobPtrs J, const float4* __restri
     } else {
       using RC = RingCert<8, 1024>;
       unsigned int ua, ub;
+      float fla, flb;
       ring_pair_search<8, 1024>(make_float4(px.L[0], px.a[0], px.b[0], px.C[0]), make_float4(px.L[1], px.a[1], px.b[1], px.C[1]),
-                                tq, lmax * 0.00138106793f, cmax * 0.001953125f, ua, ub);
+                                tq, lmax * 0.00138106793f, cmax * 0.001953125f, ua, ub, fla, flb);
       certified[0] = (ua & RC::CERT_MASK) == RC::CERT_ONE;
       certified[1] = (ub & RC::CERT_MASK) == RC::CERT_ONE;
       idx[0] = (ua & RC::IDX_MASK) / 1024;

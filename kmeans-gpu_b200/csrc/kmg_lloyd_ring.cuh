@@ -86,9 +86,10 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 // One pixel into (SIGN = +1) or out of (SIGN = -1) the private slots of a cluster: three biased
 // fixed-point values and the count, four fire-and-forget shared-memory reductions.
-template <unsigned int SPAN, int SIGN = 1>
+// L_BIASED: the first value already is L + FIXED_MAGIC.
+template <unsigned int SPAN, int SIGN = 1, bool L_BIASED = false>
 __device__ __forceinline__ void slot_add(uint32_t addr, float L, float a, float b) {
-  const unsigned int f0 = __float_as_uint(__fadd_rn(L, FIXED_MAGIC)), f1 = __float_as_uint(__fadd_rn(a, FIXED_MAGIC)),
+  const unsigned int f0 = __float_as_uint(L_BIASED ? L : __fadd_rn(L, FIXED_MAGIC)), f1 = __float_as_uint(__fadd_rn(a, FIXED_MAGIC)),
                      f2 = __float_as_uint(__fadd_rn(b, FIXED_MAGIC));
   asm volatile(
       "red.shared.add.u32 [%0], %1;\n"
@@ -112,7 +113,8 @@ struct RingCert {
 };
 template <int KT, unsigned int STRIDE>
 __device__ __forceinline__ void ring_pair_search(const float4& va, const float4& vb, const float (&tq)[KT][6], float lmax_u,
-                                                 float cmax_v, unsigned int& ua, unsigned int& ub) {
+                                                 float cmax_v, unsigned int& ua, unsigned int& ub, float& fixed_la,
+                                                 float& fixed_lb) {
   constexpr float TOTAL = (float)(KT * KT + KT * (KT - 1) / 2);  // sum of all weights (KT + j)
   constexpr float WSCALE = (float)STRIDE;
   const fast::PixCoef ca = fast::pix_coef(va.x, va.y, va.z, va.w);
@@ -134,11 +136,13 @@ __device__ __forceinline__ void ring_pair_search(const float4& va, const float4&
   mb = fast::min3(mb, sb[5], sb[6]);
   ma = fminf(ma, sa[7]);
   mb = fminf(mb, sb[7]);
-  // threshold = minimum + fast::score_eps, the addition folded into the last FMA
-  // (|L| * 2^-9.5 = |L * 2^-9| * 2^-0.5)
-  const float ua_ = fmaf(fabsf(la), 0.70710678f, lmax_u), va_ = fmaf(va.w, 0.001953125f, cmax_v);
-  const float ub_ = fmaf(fabsf(lb), 0.70710678f, lmax_u), vb_ = fmaf(vb.w, 0.001953125f, cmax_v);
-  const float ta = fmaf(ua_, ua_, fmaf(va_, va_, ma)), tb = fmaf(ub_, ub_, fmaf(vb_, vb_, mb));
+  // threshold = minimum + fast::score_eps, the addition folded into the last FMA, both pixels at once:
+  // u = L * 2^-9.5 + lmax * 2^-9.5 from the pair that already holds L * 2^-9 (L >= 0 in both colour
+  // spaces; a rounding-sized negative L would shrink the bound by parts in 10^9), v = C * 2^-9 + cmax * 2^-9
+  const fast::f32x2 u2 = fast::fma2(pp[0], fast::pack2(0.70710678f, 0.70710678f), fast::pack2(lmax_u, lmax_u));
+  const fast::f32x2 v2 = fast::pack2(fmaf(va.w, 0.001953125f, cmax_v), fmaf(vb.w, 0.001953125f, cmax_v));
+  float ta, tb;
+  fast::unpack2(fast::fma2(u2, u2, fast::fma2(v2, v2, fast::pack2(ma, mb))), ta, tb);
   // V = sum_j (KT + j) * stride * [s_j <= t]: exactly one score within eps of the minimum  <=>
   // V == (KT + idx) * stride, and then V & IDX_MASK is the byte offset of cluster idx's slot
   fast::f32x2 acc0 = fast::pack2(8388608.0f + TOTAL * WSCALE, 8388608.0f + TOTAL * WSCALE);
@@ -157,6 +161,8 @@ __device__ __forceinline__ void ring_pair_search(const float4& va, const float4&
   fast::unpack2(fast::add2(acc0, acc1), Va, Vb);
   ua = __float_as_uint(Va);
   ub = __float_as_uint(Vb);
+  // rint(L * 2^15) of both pixels from the pair L * 2^-9: (L * 2^-9) * 512 + 384 = L + 384, one rounding
+  fast::unpack2(fast::fma2(pp[0], fast::pack2(512.0f, 512.0f), fast::pack2(FIXED_MAGIC, FIXED_MAGIC)), fixed_la, fixed_lb);
 }
 
 // The exact path for one pixel of the stage that left the hot loop (cold; every lane of the warp
@@ -321,11 +327,12 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
 #pragma unroll
         for (int h = 0; h < P / 2; ++h) {
           unsigned int ua, ub;
-          ring_pair_search<KT, CTHREADS * 4>(v[2 * h], v[2 * h + 1], tq, lmax_u, cmax_v, ua, ub);
+          float fla, flb;
+          ring_pair_search<KT, CTHREADS * 4>(v[2 * h], v[2 * h + 1], tq, lmax_u, cmax_v, ua, ub, fla, flb);
           // every pixel goes to the slot its flag sum points at; the rare uncertified one is moved by
           // the exact path below (no predicate, no branch around the reductions)
-          slot_add<L::SLOT_SPAN>((ua & IDX_MASK) | slot_tid_u32, v[2 * h].x, v[2 * h].y, v[2 * h].z);
-          slot_add<L::SLOT_SPAN>((ub & IDX_MASK) | slot_tid_u32, v[2 * h + 1].x, v[2 * h + 1].y, v[2 * h + 1].z);
+          slot_add<L::SLOT_SPAN, 1, true>((ua & IDX_MASK) | slot_tid_u32, fla, v[2 * h].y, v[2 * h].z);
+          slot_add<L::SLOT_SPAN, 1, true>((ub & IDX_MASK) | slot_tid_u32, flb, v[2 * h + 1].y, v[2 * h + 1].z);
           all_cert &= (ua & CERT_MASK) == CERT_ONE && (ub & CERT_MASK) == CERT_ONE;
           hit[2 * h] = ua;
           hit[2 * h + 1] = ub;
