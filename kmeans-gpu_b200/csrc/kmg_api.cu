@@ -65,6 +65,8 @@ static const LloydVariant LLOYD_VARIANTS[] = {
     {LVR(2, 8, 2), "TMA ring 8 x 8 KiB, 2 px per lane and stage, 2 blocks/SM"},
     {LVR(2, 4, 3), "TMA ring 4 x 8 KiB, 3 blocks/SM"},
     {LVR(8, 2, 2), "TMA ring 2 x 32 KiB, 2 blocks/SM"},
+    {LVR(4, 2, 3), "TMA ring 2 x 16 KiB, 3 blocks/SM"},
+    {LVR(4, 2, 2), "TMA ring 2 x 16 KiB, 2 blocks/SM"},
     {LVRF(2, 8, 2, 8), "TMA ring 8 x 8 KiB, memory side alone (timing experiment, sums dropped)"},
     // k <= 16
     {LV16(2, 2, true, true), "const table, atomic slots, 256 thr x 2 px, 2 blocks/SM"},

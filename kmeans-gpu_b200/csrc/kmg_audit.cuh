@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) k_audit(JobPtrs J, const float4* __restri
 #pragma unroll
       for (int q = 0; q < 6; ++q) tq[j][q] = rec_at(s_tab, j)->q[q];
       tq[j][1] = __int_as_float(__float_as_int(tq[j][1]) + (9 << 23));
+      tq[j][3] = __int_as_float(__float_as_int(tq[j][3]) + (9 << 23));
     }
   }
   constexpr bool CONV = MODE != 0;

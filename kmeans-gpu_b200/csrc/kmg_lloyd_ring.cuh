@@ -101,7 +101,8 @@ __device__ __forceinline__ void slot_add(uint32_t addr, float L, float a, float 
       : "memory");
 }
 
-// The certified search of one pixel pair against the resident table (tq[j][1] carries -Lc * 2^9).
+// The certified search of one pixel pair against the resident table (tq[j][1] and tq[j][3] carry
+// -Lc * 2^9 and C2 * 2^9).
 // Returns, per pixel, the bits of 2^23 + V with V = sum_j (KT + j) * STRIDE * [s_j <= min + eps]:
 // exactly one score within eps of the minimum  <=>  (V & CERT_MASK) == CERT_ONE, and then
 // V & IDX_MASK = idx * STRIDE, the byte offset of cluster idx's slot.
@@ -117,15 +118,26 @@ __device__ __forceinline__ void ring_pair_search(const float4& va, const float4&
                                                  float& fixed_lb) {
   constexpr float TOTAL = (float)(KT * KT + KT * (KT - 1) / 2);  // sum of all weights (KT + j)
   constexpr float WSCALE = (float)STRIDE;
-  const fast::PixCoef ca = fast::pix_coef(va.x, va.y, va.z, va.w);
-  const fast::PixCoef cb = fast::pix_coef(vb.x, vb.y, vb.z, vb.w);
+  // The per-pixel coefficients of the reduced score (fast::pix_coef) for both pixels at once, in
+  // packed arithmetic wherever the operands already sit in register pairs.  L and the pixel's
+  // chroma travel as L * 2^-9 and C * 2^-9 against table entries scaled by 2^9 (all exact): the pairs
+  // then are results of multiplications — a pair merely put together from two loads is cloned by
+  // ptxas before almost every use (ten moves per pixel pair).
   fast::f32x2 pp[5];
-  pack_coefs(ca, cb, pp);
-  // L travels as L * 2^-9 against a table entry scaled by 2^9 (both exact): the pair then is the
-  // result of two multiplications — a pair merely put together from the two loads is cloned by
-  // ptxas before almost every use (ten moves per pixel pair)
-  const float la = va.x * 0.001953125f, lb = vb.x * 0.001953125f;
-  pp[0] = fast::pack2(la, lb);
+  pp[0] = fast::pack2(va.x * 0.001953125f, vb.x * 0.001953125f);
+  const fast::f32x2 c2 = fast::pack2(va.w * 0.001953125f, vb.w * 0.001953125f);
+  const fast::f32x2 one2 = fast::pack2(1.0f, 1.0f);
+  float sca, scb, sha, shb;
+  fast::unpack2(fast::fma2(c2, fast::pack2(0.045f * 512.0f, 0.045f * 512.0f), one2), sca, scb);  // SC = 1 + 0.045 C
+  fast::unpack2(fast::fma2(c2, fast::pack2(0.015f * 512.0f, 0.015f * 512.0f), one2), sha, shb);  // SH = 1 + 0.015 C
+  const fast::f32x2 rsc = fast::pack2(fast::rcp(sca), fast::rcp(scb)), rsh = fast::pack2(fast::rcp(sha), fast::rcp(shb));
+  pp[1] = fast::mul2(rsc, rsc);                          // 1 / SC^2
+  const fast::f32x2 hs2 = fast::mul2(rsh, rsh);          // 1 / SH^2
+  pp[2] = fast::mul2(c2, fast::sub2(hs2, pp[1]));        // C (1/SH^2 - 1/SC^2) * 2^-9
+  float hsa, hsb;
+  fast::unpack2(hs2, hsa, hsb);
+  pp[3] = fast::pack2(hsa * va.y, hsb * vb.y);           // a / SH^2
+  pp[4] = fast::pack2(hsa * va.z, hsb * vb.z);           // b / SH^2
   float sa[KT], sb[KT];
 #pragma unroll
   for (int j = 0; j < KT; ++j) fast::unpack2(score2(pp, tq[j]), sa[j], sb[j]);
@@ -140,7 +152,7 @@ __device__ __forceinline__ void ring_pair_search(const float4& va, const float4&
   // u = L * 2^-9.5 + lmax * 2^-9.5 from the pair that already holds L * 2^-9 (L >= 0 in both colour
   // spaces; a rounding-sized negative L would shrink the bound by parts in 10^9), v = C * 2^-9 + cmax * 2^-9
   const fast::f32x2 u2 = fast::fma2(pp[0], fast::pack2(0.70710678f, 0.70710678f), fast::pack2(lmax_u, lmax_u));
-  const fast::f32x2 v2 = fast::pack2(fmaf(va.w, 0.001953125f, cmax_v), fmaf(vb.w, 0.001953125f, cmax_v));
+  const fast::f32x2 v2 = fast::add2(c2, fast::pack2(cmax_v, cmax_v));
   float ta, tb;
   fast::unpack2(fast::fma2(u2, u2, fast::fma2(v2, v2, fast::pack2(ma, mb))), ta, tb);
   // V = sum_j (KT + j) * stride * [s_j <= t]: exactly one score within eps of the minimum  <=>
@@ -170,11 +182,10 @@ __device__ __forceinline__ void ring_pair_search(const float4& va, const float4&
 // the byte offset of a cluster): an uncertified pixel is taken out of that slot again and put into
 // the cluster the exact search finds.
 template <unsigned int SPAN>
-__device__ __noinline__ void ring_slow_pixel(const CentRec* __restrict__ g_tab, unsigned int k, uint32_t px_addr, bool nd,
+__device__ __noinline__ void ring_slow_pixel(const CentRec* __restrict__ g_tab, unsigned int k, float4 v, bool nd,
                                              uint32_t hit, float lmax, float cmax, uint32_t slot_tid_u32,
                                              unsigned int cluster_stride, unsigned int& slow) {
   if (!__any_sync(0xffffffffu, nd)) return;
-  const float4 v = lds128(px_addr);
   const float eps = fast::score_eps(v.x, v.w, lmax, cmax);
   const unsigned int idx = warp_exact_argmin<true>(g_tab, k, nd, v.x, v.y, v.z, v.w, eps, 0u);
   if (nd) {
@@ -270,6 +281,7 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
         // -Lc * 2^9 by an integer addition to the exponent field (stays in the uniform datapath; a zero
         // becomes 2^-118, which still multiplies to nothing)
         tq[j][1] = __int_as_float(__float_as_int(tq[j][1]) + (9 << 23));
+        tq[j][3] = __int_as_float(__float_as_int(tq[j][3]) + (9 << 23));  // C2 * 2^9 likewise
       }
     }
     const float lmax_u = lmax * 0.00138106793f, cmax_v = cmax * 0.001953125f;  // see fast::score_eps
@@ -310,6 +322,7 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
       const unsigned int t_stop = min(my_tiles, t + (FLUSH_PX - since_flush) / P);
       const unsigned int t_begin = t;
       unsigned int need = 0, hit[P];
+      float4 vk[P];  // the pixels of the stage that left the loop (its ring slot has been handed back)
       // ---- hot loop: one stage (P / 2 pixel pairs per lane) per iteration, no calls, table resident ----
       for (; t < t_stop; ++t) {
         const unsigned int s = t & (D - 1);
@@ -318,9 +331,18 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
         float4 v[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) v[i] = lds128(stage_addr + i * 512);
+        // The pixels are in registers: hand the stage back at once (not after the arithmetic), so the
+        // refill is in flight while this warp computes.  The arrive must not overtake the loads: its
+        // address is made to depend on the last value of every one of them (chroma >= 0: the sign bits
+        // are 0), which makes the hardware wait for the data first.
+        {
+          unsigned int dep = 0;
+#pragma unroll
+          for (int i = 0; i < P; ++i) dep |= __float_as_uint(v[i].w);
+          if (lane == 0) mbar_arrive(empty_u32 + s * 8 + (dep >> 31));
+        }
         if (FLAGS & 8) {  // timing experiment: the memory side alone
           if (v[0].x + v[P - 1].x == 12345.678f) slow++;
-          if (lane == 0) mbar_arrive(empty_u32 + s * 8);
           continue;
         }
         bool all_cert = true;
@@ -339,20 +361,20 @@ __global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
         }
         if (__any_sync(0xffffffffu, !all_cert)) {
 #pragma unroll
-          for (int i = 0; i < P; ++i) need |= ((hit[i] & CERT_MASK) == CERT_ONE ? 0u : 1u) << i;
+          for (int i = 0; i < P; ++i) {
+            need |= ((hit[i] & CERT_MASK) == CERT_ONE ? 0u : 1u) << i;
+            vk[i] = v[i];
+          }
           break;
         }
-        if (lane == 0) mbar_arrive(empty_u32 + s * 8);  // stage consumed by this warp
       }
       // ---- cold: exact path of the stage that left the loop, slot flush ------------------------------
       if (t < t_stop) {
-        const unsigned int s = t & (D - 1);
 #pragma unroll
         for (int i = 0; i < P; ++i)
-          ring_slow_pixel<L::SLOT_SPAN>(J.tab, k, ring_lane_u32 + s * L::STAGE_BYTES + i * 512, (need >> i) & 1u,
-                                        hit[i] & IDX_MASK, lmax, cmax, slot_tid_u32, CTHREADS * 4, slow);
+          ring_slow_pixel<L::SLOT_SPAN>(J.tab, k, vk[i], (need >> i) & 1u, hit[i] & IDX_MASK, lmax, cmax, slot_tid_u32,
+                                        CTHREADS * 4, slow);
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty_u32 + s * 8);
         ++t;
       }
       since_flush += P * (t - t_begin);

@@ -230,7 +230,7 @@ def test_block_accumulators_drain_mid_pass(K, D, oracle, torch, monkeypatch):
         p.close()
 
 
-@pytest.mark.parametrize("k,env,n_variants", [(7, "KMG_LLOYD8_VARIANT", 11), (13, "KMG_LLOYD16_VARIANT", 4),
+@pytest.mark.parametrize("k,env,n_variants", [(7, "KMG_LLOYD8_VARIANT", 13), (13, "KMG_LLOYD16_VARIANT", 4),
                                               (27, "KMG_LLOYD32_VARIANT", 2)])
 def test_every_lloyd_variant_gives_the_same_sums(K, D, oracle, torch, monkeypatch, k, env, n_variants):
     """LLOYD_VARIANTS (kmg_api.cu): shared-memory or constant-bank table, atomic or read-modify-write
