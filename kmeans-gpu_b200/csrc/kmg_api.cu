@@ -283,6 +283,7 @@ struct kmg_job {
   int color_space = 0;
   kmg_opts opts{};
   // shard of a distributed image
+  const uint8_t* rgba_src = nullptr;  // set: the work plane is still to be written by the first init round (fused conversion)
   bool sharded = false;
   uint32_t global_w = 0, global_h = 0, row_offset = 0;
   float* d_xfer = nullptr;  // 4 floats, colour broadcast during distributed init
@@ -932,7 +933,13 @@ static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cud
 #if KMG_HAVE_NCCL_HEADER
   if (dist) CU(cudaMemsetAsync(j->d_xfer, 0, 16, s));
 #endif
-  k_init_seed<<<1, 32, 0, s>>>(j->P, j->work, seed_local ? seed - offset : 0ull, seed_local ? 1 : 0);
+  const uint32_t* rgba_src = (const uint32_t*)j->rgba_src;
+  if (rgba_src && (dist || j->k < 2)) {  // no fused first round on these paths: convert now
+    TRY(launch_convert(ctx, j->rgba_src, n, j->color_space, (float*)j->work, s));
+    rgba_src = nullptr;
+  }
+  k_init_seed<<<1, 32, 0, s>>>(j->P, j->work, seed_local ? seed - offset : 0ull, seed_local ? 1 : 0, rgba_src, ctx->d_lut,
+                               j->color_space);
   LAUNCHED(ctx);
   CHECK_LAUNCH();
 #if KMG_HAVE_NCCL_HEADER
@@ -973,6 +980,9 @@ static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cud
         k_init_round<true, 2><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X, ub);
       else if (fused)
         k_init_round<false, 2><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X, ub);
+      else if (c == 1 && rgba_src)
+        k_init_round<true, 1, true><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X, ub, rgba_src,
+                                                         (float4*)j->work, ctx->d_lut, j->color_space);
       else if (c == 1)
         k_init_round<true, 1><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X, ub);
       else
@@ -990,7 +1000,10 @@ static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cud
   } else
   for (uint32_t c = 1; c < j->k; ++c) {
     if (!dist) {
-      if (c == 1)
+      if (c == 1 && rgba_src)
+        k_init_round<true, 1, true><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X, nullptr, rgba_src,
+                                                         (float4*)j->work, ctx->d_lut, j->color_space);
+      else if (c == 1)
         k_init_round<true, 1><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
       else
         k_init_round<false, 1><<<grid, 256, 0, s>>>(j->P, j->work, j->dmin, n, offset, c, X);
@@ -1541,8 +1554,11 @@ static int kmeans_on_device(kmg_ctx* ctx, Workspace* ws, const uint8_t* d_rgba, 
   }
   TRY(ws->work.ensure(n * 16));
   TRY(ws->dmin.ensure(dmin_bytes(n)));
-  if (!plane_ready) TRY(launch_convert(ctx, img, n, cs, (float*)ws->work.p, s));
+  // the first consumer of the plane is the first init round: the conversion is fused into it (k >= 2)
+  const bool fuse_convert = !plane_ready && k >= 2;
+  if (!plane_ready && !fuse_convert) TRY(launch_convert(ctx, img, n, cs, (float*)ws->work.p, s));
   TRY(job_setup(job, ctx, (const float*)ws->work.p, iw, ih, k, cs, o, ws->blob.p, (float*)ws->dmin.p, ws->h_state, s));
+  job->rgba_src = fuse_convert ? img : nullptr;
   TRY(job_init_impl(job, nullptr, nullptr, s));
   TRY(job_run_impl(job, nullptr, s));
   if (prepared) *prepared = false;

@@ -585,22 +585,37 @@ __device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1/K3: RGBA8 -> work plane, exact.  4 pixels (one 128-bit load) per thread per step.
+// K1/K3: RGBA8 -> work plane, exact (rgb_to_lab.wgsl:11-80, rgb8u_to_rgb32f.wgsl:4-17).
+// Four pixels per thread and step, lane-consecutive within each of the four (so every load
+// instruction of a warp reads 128 contiguous bytes and every store instruction writes 512), all four
+// loads issued before the first conversion starts and the four conversions independent of each other:
+// the kernel was a latency-bound stream with one dependent load -> ~150 instructions -> store per
+// thread (0.44 of the HBM peak); what remains is the arithmetic of the exact cube root.
 __global__ void __launch_bounds__(256) k_convert(const uint32_t* __restrict__ rgba, unsigned long long n,
                                                  int color_space, const float* __restrict__ lut_g,
                                                  float4* __restrict__ work) {
   __shared__ float lut[256];
   lut[threadIdx.x] = lut_g[threadIdx.x];
   __syncthreads();
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    uint32_t v = __ldcs(rgba + p);
-    float4 o;
-    if (color_space == 0)
-      o = ex::lin100_to_lab(lut[v & 255u], lut[(v >> 8) & 255u], lut[(v >> 16) & 255u]);
-    else
-      o = ex::rgb8_to_rgbf(v);
-    work[p] = o;
+  constexpr int U = 4;
+  const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x * U;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x * U + threadIdx.x; base < n; base += step) {
+    uint32_t v[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned long long p = base + (unsigned long long)i * blockDim.x;
+      v[i] = p < n ? __ldcs(rgba + p) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned long long p = base + (unsigned long long)i * blockDim.x;
+      float4 o;
+      if (color_space == 0)
+        o = ex::lin100_to_lab(lut[v[i] & 255u], lut[(v[i] >> 8) & 255u], lut[(v[i] >> 16) & 255u]);
+      else
+        o = ex::rgb8_to_rgbf(v[i]);
+      if (p < n) __stcs(work + p, o);
+    }
   }
 }
 
@@ -680,11 +695,21 @@ __device__ __forceinline__ unsigned long long key_to_pixel(unsigned long long ke
   return (key >> 32) == 0ull ? 0ull : ((key & 0xffffffffull) ^ 15ull);
 }
 
+// rgba != NULL: the work plane does not exist yet (the first init round will write it, fused with the
+// conversion): the seed pixel is converted here.
 __global__ void k_init_seed(JobPtrs J, const float4* __restrict__ work, unsigned long long seed_local,
-                            int seed_is_local) {
+                            int seed_is_local, const uint32_t* __restrict__ rgba = nullptr,
+                            const float* __restrict__ lut_g = nullptr, int color_space = 0) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (seed_is_local) {
-      float4 v = work[seed_local];
+      float4 v;
+      if (rgba) {
+        const uint32_t px = rgba[seed_local];
+        v = color_space == 0 ? ex::lin100_to_lab(lut_g[px & 255u], lut_g[(px >> 8) & 255u], lut_g[(px >> 16) & 255u])
+                             : ex::rgb8_to_rgbf(px);
+      } else {
+        v = work[seed_local];
+      }
       J.cent[0] = make_float4(v.x, v.y, v.z, 1.0f);
     }
     for (unsigned int i = 0; i < J.st->k; ++i) J.keys[i] = 0ull;
@@ -709,13 +734,26 @@ __global__ void k_init_seed(JobPtrs J, const float4* __restrict__ work, unsigned
 //   seq_base - j, disjoint from the passes' seq_base + pass + 1.
 // ub (may be NULL): the 16-bit upper bounds of the running minima, kept up to date for the lazy
 // rounds that follow (kmg_init_lazy.cuh).
-template <bool FIRST, int PICK>
+// CONVERT (with FIRST): the first consumer of the work plane is this round, so the conversion is
+// fused into it (operations.rs:63-83 runs convert -> init -> assign as separate dispatches): RGBA8 in
+// (4 B/px), work plane + running minimum out (20 B/px) instead of a convert sweep (20 B/px) followed by a
+// round that reads the plane again (16 + 4 B/px).
+template <bool FIRST, int PICK, bool CONVERT = false>
 __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __restrict__ work,
                                                     float* __restrict__ dmin, unsigned long long n,
                                                     unsigned long long pixel_offset, unsigned int j, PeerXchg X,
-                                                    unsigned short* __restrict__ ub = nullptr) {
+                                                    unsigned short* __restrict__ ub = nullptr,
+                                                    const uint32_t* __restrict__ rgba = nullptr,
+                                                    float4* __restrict__ work_out = nullptr,
+                                                    const float* __restrict__ lut_g = nullptr, int color_space = 0) {
+  static_assert(!CONVERT || FIRST, "the conversion is fused into the first round only");
   __shared__ unsigned long long s_key[8];
   __shared__ bool s_last;
+  __shared__ float lut[CONVERT ? 256 : 1];
+  if (CONVERT) {
+    lut[threadIdx.x] = lut_g[threadIdx.x];
+    __syncthreads();
+  }
   // centroid j-1 was resolved into J.cent[j-1] by the previous round (or k_init_seed for j == 1).
   const float4 c = J.cent[j - 1];
   const float cc = ex::chroma(c.y, c.z);
@@ -732,7 +770,14 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
     for (int i = 0; i < U; ++i) {
       const unsigned long long p = base + (unsigned long long)i * blockDim.x;
       const bool ok = p < n;
-      v[i] = ok ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (CONVERT) {
+        const uint32_t px = ok ? __ldcs(rgba + p) : 0u;
+        v[i] = color_space == 0 ? ex::lin100_to_lab(lut[px & 255u], lut[(px >> 8) & 255u], lut[(px >> 16) & 255u])
+                                : ex::rgb8_to_rgbf(px);
+        if (ok) work_out[p] = v[i];
+      } else {
+        v[i] = ok ? ldg_stream(work + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       old[i] = (!FIRST && ok) ? dmin[p] : 1000000.0f;
     }
 #pragma unroll
@@ -777,7 +822,7 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
     key = __ldcg(J.keys + j);
     pix = key_to_pixel(key);
     if (pix >= pixel_offset && pix - pixel_offset < n) {
-      const float4 v = work[pix - pixel_offset];
+      const float4 v = CONVERT ? __ldcg(work_out + (pix - pixel_offset)) : work[pix - pixel_offset];
       col = make_float4(v.x, v.y, v.z, 1.0f);
     } else {
       pix = ~0ull;  // zero maximum on a shard that does not hold pixel 0: no candidate
