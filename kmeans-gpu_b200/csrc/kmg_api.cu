@@ -754,9 +754,13 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
       if (j->cslot < 0) v = ctx->lloyd_nocst[cls];  // no free slot in the constant bank: shared-memory table
     }
     const LloydVariant& V = LLOYD_VARIANTS[v];
-    if (V.const_tab)  // the table of this pass goes to the job's slot of the constant bank (see c_tab)
-      CU(cudaMemcpyAsync((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4, j->P.tab,
-                         (size_t)V.kcap * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
+    if (V.const_tab && !j->P.ctab) {
+      // first pass with a slot: the current table goes to the job's slot of the constant bank once; from
+      // then on build_table (k_prepare, the last block of every pass) keeps the slot up to date itself
+      float* slot = (float*)((char*)ctx->c_tab_dev + (size_t)j->cslot * CTAB_FLOATS * 4);
+      CU(cudaMemcpyAsync(slot, j->P.tab, (size_t)V.kcap * sizeof(CentRec), cudaMemcpyDeviceToDevice, s));
+      j->P.ctab = slot;
+    }
     int grid = grid_for(ctx, n, (V.threads == 288 ? 256 : V.threads) * V.px, ctx->occ_lloyd[v]);
     V.fn<<<grid, V.threads, V.smem, s>>>(j->P, j->work, n, j->color_space, partial, X, V.const_tab ? j->cslot : 0, j->k);
   } else {

@@ -62,6 +62,9 @@ struct JobPtrs {
   unsigned long long* keys;    // k  — arg-max keys of the init rounds
   uint32_t* pal;               // k  — centroids reverted to RGBA8
   unsigned int acc_copies;     // privatised accumulator copies (block b adds into copy b % acc_copies)
+  float* ctab;                 // the job's slot of the constant-bank table c_tab, addressed as global memory
+                               // (NULL: none): build_table refreshes it, so that no copy has to be enqueued
+                               // between two passes (constant caches are invalidated at kernel boundaries)
 };
 
 __host__ __device__ inline unsigned int pad32(unsigned int k) { return (k + 31u) & ~31u; }
@@ -128,6 +131,7 @@ __device__ __forceinline__ JobPtrs job_at(JobPtrs J, size_t off) {
   R.keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(J.keys) + off);
   R.pal = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(J.pal) + off);
   R.acc_copies = J.acc_copies;
+  R.ctab = nullptr;
   return R;
 }
 
@@ -152,7 +156,8 @@ __device__ __forceinline__ void tab_to_smem(CentRec* s_tab, const CentRec* __res
 // it, which buys a third resident block per SM.  The host copies J.tab into the job's slot
 // (device-to-device, 24 k bytes) before each pass.
 constexpr int CTAB_SLOTS = 64;
-constexpr int CTAB_FLOATS = 16 * 6;
+constexpr int CTAB_RECORDS = 16;
+constexpr int CTAB_FLOATS = CTAB_RECORDS * 6;
 __constant__ float c_tab[CTAB_SLOTS][CTAB_FLOATS];
 // (Feeding the chunk loop of the k > 32 search from the constant bank the same way was measured
 // slower — 48 uniform registers per chunk leave no room to prefetch the next chunk — and removed.)
@@ -224,6 +229,10 @@ __device__ void build_table(const JobPtrs& J, unsigned int k, int color_space, b
       r.q[1] = r.q[2] = r.q[3] = r.q[4] = r.q[5] = 0.0f;
     }
     J.tab[c] = r;
+    if (J.ctab && c < CTAB_RECORDS) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) J.ctab[6 * c + q] = r.q[q];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
