@@ -238,3 +238,20 @@ def test_rust_shim_matches_header():
     for f in re.findall(r'"(kmg_[a-z_]+\.(?:cuh|cu|cpp))"', build):
         assert f in csrc, f"build.rs names {f}, which is not in kmeans-gpu_b200/csrc"
     assert {p.name for p in (ROOT / "kmeans-gpu_b200" / "csrc").glob("*.cuh")} <= set(re.findall(r'"(kmg_[a-z_]+\.cuh)"', build))
+
+
+def test_all_16m_colours_round_trip_through_lab(native_lib):
+    """R8 pin, widened: every one of the 2^24 sRGB8 colours must survive sRGB8 -> Lab (kmg_fixed_centroids,
+    the `palette` crate's conversion behind CentroidsBuffer::fixed_centroids, structures.rs:523-553) -> sRGB8
+    (kmg_centroids_to_rgba8, pull_values, :600-617) unchanged — the property the reference relies on when a
+    fixed palette comes back out of `find`, and the tightest check available for a crate whose source is
+    not in the tree (the three bit-exact goldens go through the same code)."""
+    import kmeans_gpu_b200 as K
+
+    step = 1 << 20
+    for lo in range(0, 1 << 24, step):
+        v = np.arange(lo, lo + step, dtype=np.uint32)
+        cols = np.stack([v & 255, (v >> 8) & 255, v >> 16, np.full_like(v, 255)], axis=1).astype(np.uint8)
+        lab = K.fixed_centroids(cols, K.ColorSpace.Lab)
+        back = K.centroids_to_rgba8(lab)
+        assert np.array_equal(back, cols), lo
