@@ -633,6 +633,38 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
     entry["e2e_gb_per_s_each_way_per_gpu"] = hn * 1920 * 1080 * 4 / dt / 1e9
     entry["e2e_what"] = f"kmg_reduce_batch on {hn} pinned host frames per GPU: chunked H2D / kernels / D2H pipeline"
     out["frames_1080p_k16_reduce_dither"] = entry
+
+    # ---- what the host side can deliver: plain page-locked copies, all ranks at once, no kernels ------
+    # (the ceiling of every end-to-end number above: kmg_reduce_batch moves 8.3 MB per frame each way)
+    nbytes = 256 << 20
+    hp_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    hp_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dv_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dv_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copies(up, down, reps=4):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    dv_in.copy_(hp_in, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_dn):
+                    hp_out.copy_(dv_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * nbytes / max_over_ranks(time.perf_counter() - t0) / 1e9
+
+    copies(True, True, 1)
+    probe = {"h2d_alone_gb_per_s_per_gpu": copies(True, False), "d2h_alone_gb_per_s_per_gpu": copies(False, True),
+             "both_ways_gb_per_s_each_way_per_gpu": copies(True, True), "n_gpus": world,
+             "what": "256 MiB page-locked copies on every rank at the same time, slowest rank counts; multiply by n_gpus "
+                     "for what the host's memory and PCIe fabric deliver in total"}
+    out["host_copy_ceiling"] = probe
+    del hp_in, hp_out, dv_in, dv_out
     return out
 
 
