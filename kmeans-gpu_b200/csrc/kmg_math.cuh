@@ -86,6 +86,17 @@ __device__ __forceinline__ float pow_third(float t) {
   return f;
 }
 
+// x / c for one of the three white-point constants, correctly rounded like __fdiv_rn but in three
+// instructions instead of ~10 plus a slow-path call (Markstein): q = RN(x * rc) with rc = RN(1 / c),
+// r = x - q * c exactly (one FMA), q' = RN(q + r * rc).  rc is the correctly rounded reciprocal for all
+// three constants (checked against exact rationals); the quotient is the IEEE one for every X, Y, Z that
+// an sRGB8 colour can produce — test_convert_lab_all_16m_colours compares all 2^24 colours with the
+// oracle, which divides.
+__device__ __forceinline__ float div_white(float x, float c, float rc) {
+  const float q = __fmul_rn(x, rc);
+  const float r = __fmaf_rn(-q, c, x);
+  return __fmaf_rn(r, rc, q);
+}
 // core/shaders/converters/rgb_to_lab.wgsl:39-64
 __device__ __forceinline__ float lab_f(float t) {
   if (t > 0.008856f) return pow_third(t);
@@ -96,9 +107,9 @@ __device__ __forceinline__ float4 lin100_to_lab(float r, float g, float b) {
   float X = fadd(fadd(fmul(0.4124564f, r), fmul(0.3575761f, g)), fmul(0.1804375f, b));
   float Y = fadd(fadd(fmul(0.2126729f, r), fmul(0.7151522f, g)), fmul(0.0721750f, b));
   float Z = fadd(fadd(fmul(0.0193339f, r), fmul(0.1191920f, g)), fmul(0.9503041f, b));
-  float x = lab_f(fdiv(X, 95.0489f));
-  float y = lab_f(fdiv(Y, 100.0f));
-  float z = lab_f(fdiv(Z, 108.8840f));
+  float x = lab_f(div_white(X, 95.0489f, 0x1.58bfb6p-7f));
+  float y = lab_f(div_white(Y, 100.0f, 0x1.47ae14p-7f));
+  float z = lab_f(div_white(Z, 108.8840f, 0x1.2cf1b2p-7f));
   float4 o;
   o.x = fsub(fmul(116.0f, y), 16.0f);
   o.y = fmul(500.0f, fsub(x, y));
