@@ -298,21 +298,20 @@ def run_ours(args):
         job.step(1)
     barrier()
     launches0 = proc.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # one event between consecutive steps (K + 1 in all): the end of step i is the start of step i + 1
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     t_wall0 = time.perf_counter()
-    t_start.record()
-    for a, b in evs:
-        a.record()
+    evs[0].record()
+    for i in range(args.steps):
         job.step(1)
-        b.record()
-    t_end.record()
+        evs[i + 1].record()
     barrier()
     t_wall1 = time.perf_counter()
     launches = proc.launch_count() - launches0
-    total_ms = t_start.elapsed_time(t_end)
-    step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)])
+    step_ms = float(np.mean(per_step))  # average launch duration of the pass kernel (event to event, one launch in between)
     clocks = sampler.stop(t_wall0, t_wall1, t_load) if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms, step_ms], device=dev, dtype=torch.float64)
