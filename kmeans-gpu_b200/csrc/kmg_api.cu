@@ -86,6 +86,7 @@ static int lloyd_variant_index(int kcap, int v) {
 }
 #define LLOYDG k_lloyd<0, 0, 256, 4, false, 2>
 #define LLOYDGS k_lloyd<0, 0, 256, 4, false, 2, false, true>  // block accumulators in shared memory
+#define LLOYDGB k_lloyd<0, 0, 256, 4, false, 2, true, true>   // same, multipliers of the chunk loop from c_big (uniform registers)
 static constexpr uint32_t LLOYDGS_MAX_K = 2048;  // table 52 KiB + accumulators 56 KiB per block
 // Whole-k-means-in-one-launch variants (kmg_small.cuh): <table/accumulator capacity, threads>
 #define SMALL8 k_kmeans_small<8, 512>
@@ -253,6 +254,8 @@ struct kmg_ctx {
   // constant-bank table slots (kmg_kernels.cuh: c_tab), handed to jobs with k <= 8
   void* c_tab_dev = nullptr;
   bool big_block_acc = true;   // KMG_LLOYDG_BLOCKACC=0: accumulate through L2 atomics instead of shared memory
+  void* c_big_dev = nullptr;   // c_big addressed as global memory
+  bool big_const = true;       // KMG_LLOYD_BIGCONST=0: chunk loop of the k > 32 pass from shared memory only
   bool init_eager = false;     // KMG_INIT_EAGER=1: one full sweep per init round instead of the lazy cooperative launch
   int init_eager_rounds = 8;   // full sweeps before the lazy launch takes over (KMG_INIT_EAGER_ROUNDS)
   uint32_t init_lazy_min_k = 32;  // lazy rounds only for k above this (KMG_INIT_LAZY_MIN_K; tests lower it)
@@ -267,6 +270,16 @@ struct CSlot {
   CSlot(const CSlot&) {}
   CSlot& operator=(const CSlot&) { return *this; }
   ~CSlot();
+};
+
+// Ownership of c_big (the large constant-bank table of the k > 32 pass): one job per device; copies of
+// a job do not own it.
+struct CBig {
+  int device = -1;  // >= 0: held
+  CBig() = default;
+  CBig(const CBig&) {}
+  CBig& operator=(const CBig&) { return *this; }
+  ~CBig();
 };
 
 struct kmg_job {
@@ -290,6 +303,8 @@ struct kmg_job {
   uint32_t xchg_base = 0;   // PeerXchg::seq_base of this job
   // slot of the constant-bank table (small-k passes), taken at the first pass, returned with the job
   CSlot cs_owner;
+  CBig cbig_owner;
+  bool cbig_tried = false;
   int cslot = -1;  // == cs_owner.slot once acquired; plain copy so that copies of the job can launch with it
   bool cslot_tried = false;
 };
@@ -297,6 +312,7 @@ struct kmg_job {
 // The constant bank belongs to the device (one copy of the module per device), not to a context:
 // the free list is per device and process-wide.
 static std::mutex g_cslot_mu;
+static bool g_cbig_taken[64];  // per device: some job holds c_big (guarded by g_cslot_mu)
 static std::vector<int> g_cslots_free[64];  // per device
 static bool g_cslots_ready[64];
 static int cslot_acquire(kmg_job* j) {
@@ -317,6 +333,12 @@ static int cslot_acquire(kmg_job* j) {
 }
 // Jobs are only dropped after the work they enqueued has been waited for (every blocking entry
 // point synchronises; kmg_job_destroy frees device memory first, which synchronises the device).
+CBig::~CBig() {
+  if (device >= 0 && device < 64) {
+    std::lock_guard<std::mutex> g(g_cslot_mu);
+    g_cbig_taken[device] = false;
+  }
+}
 CSlot::~CSlot() {
   if (slot >= 0) {
     std::lock_guard<std::mutex> g(g_cslot_mu);
@@ -609,6 +631,9 @@ static int ctx_setup(kmg_ctx* ctx, const cudaDeviceProp& prop) {
   CU(cudaFuncSetAttribute(k_remap_meld, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_K * 16));
   small_probe(ctx, prop);
   CU(cudaGetSymbolAddress(&ctx->c_tab_dev, c_tab));
+  CU(cudaGetSymbolAddress(&ctx->c_big_dev, c_big));
+  if (const char* e = getenv("KMG_LLOYD_BIGCONST")) ctx->big_const = atoi(e) != 0;
+  CU(cudaFuncSetAttribute(LLOYDGB, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   if (const char* e = getenv("KMG_LLOYDG_BLOCKACC")) ctx->big_block_acc = atoi(e) != 0;
   if (const char* e = getenv("KMG_INIT_EAGER")) ctx->init_eager = atoi(e) != 0;
   if (const char* e = getenv("KMG_INIT_EAGER_ROUNDS")) ctx->init_eager_rounds = std::max(1, atoi(e));
@@ -769,6 +794,24 @@ static int launch_lloyd(kmg_job* j, cudaStream_t s) {
     if (j->k <= LLOYDGS_MAX_K && ctx->big_block_acc) {
       smem += (size_t)7 * pad32(j->k) * 4;
       grid = grid_for(ctx, n, 256 * 4, smem > 100 * 1024 ? 1 : 2);
+      // c_big: one job per device at a time; the first pass that gets it copies the current table over
+      // (rearranged by k_big_table), later passes find it refreshed by build_table
+      if (ctx->big_const && pad32(j->k) <= CBIG_MAX_K && !j->P.cbig && !j->cbig_tried && ctx->device < 64) {
+        j->cbig_tried = true;
+        std::lock_guard<std::mutex> g(g_cslot_mu);
+        if (!g_cbig_taken[ctx->device]) {
+          g_cbig_taken[ctx->device] = true;
+          j->cbig_owner.device = ctx->device;
+          j->P.cbig = (float*)ctx->c_big_dev;
+        }
+        if (j->P.cbig) {
+          k_big_table<<<(pad32(j->k) + 255) / 256, 256, 0, s>>>(j->P, pad32(j->k));
+          LAUNCHED(ctx);
+        }
+      }
+      if (j->P.cbig)
+        LLOYDGB<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0, j->k);
+      else
       LLOYDGS<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, ctx->block_flush_log2, j->k);
     } else {
       LLOYDG<<<grid, 256, smem, s>>>(j->P, j->work, n, j->color_space, partial, X, 0, j->k);

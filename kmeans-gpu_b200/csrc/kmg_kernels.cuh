@@ -62,6 +62,7 @@ struct JobPtrs {
   unsigned long long* keys;    // k  — arg-max keys of the init rounds
   uint32_t* pal;               // k  — centroids reverted to RGBA8
   unsigned int acc_copies;     // privatised accumulator copies (block b adds into copy b % acc_copies)
+  float* cbig;                 // c_big addressed as global memory when this job holds it (NULL otherwise)
   float* ctab;                 // the job's slot of the constant-bank table c_tab, addressed as global memory
                                // (NULL: none): build_table refreshes it, so that no copy has to be enqueued
                                // between two passes (constant caches are invalidated at kernel boundaries)
@@ -132,6 +133,7 @@ __device__ __forceinline__ JobPtrs job_at(JobPtrs J, size_t off) {
   R.pal = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(J.pal) + off);
   R.acc_copies = J.acc_copies;
   R.ctab = nullptr;
+  R.cbig = nullptr;
   return R;
 }
 
@@ -159,6 +161,13 @@ constexpr int CTAB_SLOTS = 64;
 constexpr int CTAB_RECORDS = 16;
 constexpr int CTAB_FLOATS = CTAB_RECORDS * 6;
 __constant__ float c_tab[CTAB_SLOTS][CTAB_FLOATS];
+// One large table (k <= CBIG_MAX_K) for the chunked search, laid out per chunk of 8 centroids as
+// [q0 x 8 | q1 x 8 | ... | q5 x 8]: the five multiplier rows of a chunk arrive with ten 128-bit
+// warp-uniform loads in uniform registers, where a packed FFMA2 reads its scalar operand without
+// touching the register-file banks of its two vector pairs (2.0 instead of 2.25-2.5 cycles per FFMA2
+// with a vector-register scalar).  One job per device holds it at a time.
+constexpr unsigned int CBIG_MAX_K = 1024;
+__constant__ float c_big[CBIG_MAX_K * 6];
 // (Feeding the chunk loop of the k > 32 search from the constant bank the same way was measured
 // slower — 48 uniform registers per chunk leave no room to prefetch the next chunk — and removed.)
 
@@ -233,6 +242,10 @@ __device__ void build_table(const JobPtrs& J, unsigned int k, int color_space, b
 #pragma unroll
       for (int q = 0; q < 6; ++q) J.ctab[6 * c + q] = r.q[q];
     }
+    if (J.cbig && c < CBIG_MAX_K) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) J.cbig[(c >> 3) * 48 + q * 8 + (c & 7u)] = r.q[q];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -277,6 +290,16 @@ __device__ void build_table(const JobPtrs& J, unsigned int k, int color_space, b
     J.st->dither_threshold = thr;
   }
   __syncthreads();
+}
+
+// The current table into c_big (chunk-major rows, see c_big) when a job acquires it between two passes.
+__global__ void __launch_bounds__(256) k_big_table(JobPtrs J, unsigned int kp) {
+  const unsigned int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < kp && c < CBIG_MAX_K) {
+    const CentRec r = J.tab[c];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) J.cbig[(c >> 3) * 48 + q * 8 + (c & 7u)] = r.q[q];
+  }
 }
 
 __global__ void __launch_bounds__(256) k_prepare(JobPtrs J, int color_space, int want_palette) {
@@ -464,7 +487,7 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
 // and second-best chunk minima.  The precise certificate then runs on the winning chunk alone, so
 // the half-rate ALU pipe sees ~1.1 min/select operations per (pixel, centroid) instead of 5 and
 // the loop is bound by the 5 FMAs of the score.
-template <int P, bool CONV>
+template <int P, bool CONV, bool BIG = false>
 __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
                                                float lmax, float cmax, float conv_k, float (&eps)[P],
                                                unsigned int (&idx)[P], bool (&certified)[P]) {
@@ -484,14 +507,68 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
     m2c[i] = 3.0e38f;
     ic[i] = 0;
   }
+  // BIG: multipliers from c_big through warp-uniform 128-bit constant loads (uniform registers), the
+  // addends through a per-thread address (vector registers: an FFMA2 takes one uniform operand).  Rows
+  // 1-2 of the next chunk are requested while rows 3-5 of this one are being used, rows 3-5 of this one
+  // while its rows 1-2 are being used, so no FFMA2 waits for the constant cache.
+  const size_t cb = BIG ? __cvta_generic_to_constant(c_big) : 0;
+  const unsigned int zero = BIG ? threadIdx.y : 0u;  // always 0, but not provably uniform
+  float q0n[8], q1n[8], q2n[8];
+  auto ldc4u = [&](float* d, size_t addr) {
+    asm volatile("ld.const.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "l"(addr));
+  };
+  if (BIG) {
+    ldc4u(q0n, cb + 4 * zero);
+    ldc4u(q0n + 4, cb + 16 + 4 * zero);
+    ldc4u(q1n, cb + 32);
+    ldc4u(q1n + 4, cb + 48);
+    ldc4u(q2n, cb + 64);
+    ldc4u(q2n + 4, cb + 80);
+  }
   for (unsigned int c = 0; c < kp; c += 8) {
     fast::f32x2 s2[8][H];
-    float f[48];
-    load_chunk(rec_at(tab, c), f);
+    if (BIG) {
+      const size_t base = cb + (size_t)(c >> 3) * 192;
+      float q3[8], q4[8], q5[8];
+      ldc4u(q3, base + 96);
+      ldc4u(q3 + 4, base + 112);
+      ldc4u(q4, base + 128);
+      ldc4u(q4 + 4, base + 144);
+      ldc4u(q5, base + 160);
+      ldc4u(q5 + 4, base + 176);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j) {
 #pragma unroll
-      for (int h = 0; h < H; ++h) s2[j][h] = score2(pp[h], f + 6 * j);
+        for (int h = 0; h < H; ++h) {
+          s2[j][h] = fast::fma2(pp[h][0], fast::pack2(q1n[j], q1n[j]), fast::pack2(q0n[j], q0n[j]));
+          s2[j][h] = fast::fma2(pp[h][1], fast::pack2(q2n[j], q2n[j]), s2[j][h]);
+        }
+      }
+      if (c + 8 < kp) {  // rows 0-2 of the next chunk
+        ldc4u(q0n, base + 192 + 4 * zero);
+        ldc4u(q0n + 4, base + 208 + 4 * zero);
+        ldc4u(q1n, base + 224);
+        ldc4u(q1n + 4, base + 240);
+        ldc4u(q2n, base + 256);
+        ldc4u(q2n + 4, base + 272);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          s2[j][h] = fast::fma2(pp[h][2], fast::pack2(q3[j], q3[j]), s2[j][h]);
+          s2[j][h] = fast::fma2(pp[h][3], fast::pack2(q4[j], q4[j]), s2[j][h]);
+          s2[j][h] = fast::fma2(pp[h][4], fast::pack2(q5[j], q5[j]), s2[j][h]);
+        }
+      }
+    } else {
+      float f[48];
+      load_chunk(rec_at(tab, c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) s2[j][h] = score2(pp[h], f + 6 * j);
+      }
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -1073,7 +1150,7 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
   if (KT > 0)
     argmin_small<P, (KT > 0 ? KT : 8), false, CT>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
   else
-    argmin_chunked<P, false>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
+    argmin_chunked<P, false, (CT && KT == 0)>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
   // one vote per tile: the exact path is rare (1e-4 .. 1e-2 of the pixels)
   bool need[P], any_need = false;
 #pragma unroll
@@ -1140,7 +1217,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lloyd(JobPtrs J, const float4
                                                          unsigned long long n, int color_space,
                                                          int distributed_mode, PeerXchg X, int cslot,
                                                          unsigned int k_arg) {
-  static_assert(!CT || (KT > 0 && KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k");
+  static_assert(!CT || KT == 0 || (KT * 6 <= CTAB_FLOATS && PRIVATE), "constant-bank tables: small compile-time k, or c_big");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(16) unsigned char s_tab_static[(KT > 0 && !CT) ? (KT / 8) * CHUNK_BYTES : 16];
   __shared__ bool s_last;
