@@ -427,7 +427,7 @@ __device__ __forceinline__ float total_eps(float eps0, float m, float lab_err, f
 template <int P, int KT, bool CONV, bool CT = false>
 __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, const Pix<P>& px, float lmax,
                                              float cmax, float conv_k, float (&eps)[P], unsigned int (&idx)[P],
-                                             bool (&certified)[P]) {
+                                             bool (&certified)[P], float* thr_out = nullptr) {
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::f32x2 pp[H][5];
@@ -479,6 +479,10 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
                                      px.L[2 * h + 1], px.C[2 * h + 1], inv_sc2[2 * h + 1], inv_sh2[2 * h + 1], cmax);
     certify_pair<KT>(sa, sb, ma, mb, eps[2 * h], eps[2 * h + 1], certified[2 * h], certified[2 * h + 1], idx[2 * h],
                      idx[2 * h + 1]);
+    if (thr_out) {  // smallest fast score + eps: what the exact path admits candidates up to
+      thr_out[2 * h] = ma + eps[2 * h];
+      thr_out[2 * h + 1] = mb + eps[2 * h + 1];
+    }
   }
 }
 
@@ -490,7 +494,7 @@ __device__ __forceinline__ void argmin_small(const CentRec* __restrict__ tab, co
 template <int P, bool CONV, bool BIG = false>
 __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, unsigned int kp, const Pix<P>& px,
                                                float lmax, float cmax, float conv_k, float (&eps)[P],
-                                               unsigned int (&idx)[P], bool (&certified)[P]) {
+                                               unsigned int (&idx)[P], bool (&certified)[P], float* thr_out = nullptr) {
   static_assert(P % 2 == 0, "pairs of pixels");
   constexpr int H = P / 2;
   fast::PixCoef pc[P];
@@ -613,6 +617,10 @@ __device__ __forceinline__ void argmin_chunked(const CentRec* __restrict__ tab, 
     certified[2 * h + 1] = cb && (m2c[2 * h + 1] - mb > eb);
     idx[2 * h] = ic[2 * h] + ia;
     idx[2 * h + 1] = ic[2 * h + 1] + ib;
+    if (thr_out) {  // the winning chunk's minimum is the smallest of all fast scores
+      thr_out[2 * h] = ma + ea;
+      thr_out[2 * h + 1] = mb + eb;
+    }
   }
 }
 
@@ -633,7 +641,10 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
-template <bool DENSE = false>
+// HAVE_BOUND: `slack` already is the absolute admission threshold (smallest fast score + eps, as the
+// search that failed to certify computed it with the same arithmetic): the first sweep over the table,
+// which only looks for that smallest score, is skipped.
+template <bool DENSE = false, bool HAVE_BOUND = false>
 __device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict__ tab, unsigned int k, bool need,
                                                        float L, float a, float b, float C, float slack,
                                                        unsigned int idx_in) {
@@ -647,11 +658,14 @@ __device__ __noinline__ unsigned int warp_exact_argmin(const CentRec* __restrict
     const float pb = __shfl_sync(0xffffffffu, b, src), pC = __shfl_sync(0xffffffffu, C, src);
     const float pslack = __shfl_sync(0xffffffffu, slack, src);
     const fast::PixCoef pc = fast::pix_coef(pL, pa, pb, pC);
-    float m = 3.0e38f;
-    for (unsigned int j = lane; j < k; j += 32) m = fminf(m, score1(pc, (DENSE ? tab + j : rec_at(tab, j))->q));
+    float bound = pslack;
+    if (!HAVE_BOUND) {
+      float m = 3.0e38f;
+      for (unsigned int j = lane; j < k; j += 32) m = fminf(m, score1(pc, (DENSE ? tab + j : rec_at(tab, j))->q));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float bound = m + pslack;
+      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      bound = m + pslack;
+    }
     unsigned long long best = ~0ull;
     for (unsigned int j = lane; j < k; j += 32) {
       const CentRec r = DENSE ? tab[j] : *rec_at(tab, j);
@@ -1144,13 +1158,13 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
     px.b[i] = v[i].z;
     px.C[i] = v[i].w;
   }
-  float eps[P];
+  float eps[P], thr[P];
   unsigned int idx[P];
   bool certified[P];
   if (KT > 0)
-    argmin_small<P, (KT > 0 ? KT : 8), false, CT>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified);
+    argmin_small<P, (KT > 0 ? KT : 8), false, CT>(s_tab, px, lmax, cmax, 0.0f, eps, idx, certified, thr);
   else
-    argmin_chunked<P, false, (CT && KT == 0)>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified);
+    argmin_chunked<P, false, (CT && KT == 0)>(s_tab, kp, px, lmax, cmax, 0.0f, eps, idx, certified, thr);
   // one vote per tile: the exact path is rare (1e-4 .. 1e-2 of the pixels)
   bool need[P], any_need = false;
 #pragma unroll
@@ -1162,8 +1176,8 @@ __device__ __forceinline__ void lloyd_tile(const CentRec* __restrict__ s_tab, co
 #pragma unroll
     for (int i = 0; i < P; ++i) {
       if (__any_sync(0xffffffffu, need[i])) {
-        idx[i] = warp_exact_argmin<(CT && KT > 0)>(x_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], eps[i],
-                                                   idx[i]);
+        idx[i] = warp_exact_argmin<(CT && KT > 0), true>(x_tab, k, need[i], px.L[i], px.a[i], px.b[i], px.C[i], thr[i],
+                                                         idx[i]);
         slow += need[i] ? 1u : 0u;
       }
     }
