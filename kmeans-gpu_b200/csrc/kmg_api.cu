@@ -407,11 +407,21 @@ static void ws_release(kmg_ctx* ctx, Workspace* w) {
   std::lock_guard<std::mutex> g(ctx->mu);
   ctx->pool.push_back(w);
 }
+// Hands the workspace back when the call returns — on every path.  An early error return can leave
+// copies to or from the CALLER's buffers in flight on any of the three streams; they are waited for
+// here, before the caller gets control back (and may free those buffers) and before another call can
+// take the workspace.  On the success paths the streams are idle already and the three calls cost
+// nothing measurable.
 struct WsGuard {
   kmg_ctx* ctx;
   Workspace* ws;
   ~WsGuard() {
-    if (ws) ws_release(ctx, ws);
+    if (!ws) return;
+    if (ws->copy_stream) cudaStreamSynchronize(ws->copy_stream);
+    if (ws->out_stream) cudaStreamSynchronize(ws->out_stream);
+    if (ws->stream) cudaStreamSynchronize(ws->stream);
+    cudaGetLastError();
+    ws_release(ctx, ws);
   }
 };
 
@@ -1442,8 +1452,12 @@ extern "C" int kmg_dev_fp32_peak(kmg_ctx* ctx, double* fma_per_second_out) {
   float* d = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   CU(cudaMalloc((void**)&d, 4));
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    if (e0) cudaEventDestroy(e0);
+    cudaFree(d);
+    cudaGetLastError();
+    return fail(KMG_ERR_CUDA, "kmg_dev_fp32_peak: cudaEventCreate failed");
+  }
   const int iters = 4096, grid = ctx->sms * 8;
   float best_ms = 1e30f;
   cudaError_t e = cudaSuccess;
