@@ -255,7 +255,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # (at N = 1 the process keeps every core: the CPU-baseline leg of the same run uses them all)
-    numa = bind_to_gpu_numa_node(local, world) if world > 1 else {"policy": "none (single GPU)"}
+    numa = (bind_to_gpu_numa_node(local, world) if world > 1 and not os.environ.get("KMG_BENCH_NO_BIND")
+            else {"policy": "none (single GPU)" if world == 1 else "none (KMG_BENCH_NO_BIND)"})
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     proc = K.ImageProcessor(local)
@@ -603,7 +604,7 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
     for f in range(nf):
         D.synth(proc, 1920 * 1080, frame=lo + f, seed=3, blobs=32, out=frames[f].view(-1, 4))
     outb = torch.empty_like(frames)
-    D.reduce_batch(proc, frames[:64], 16, K.ReduceMode.Dither, out=outb[:64])  # warm-up (workspace allocation)
+    D.reduce_batch(proc, frames, 16, K.ReduceMode.Dither, out=outb)  # warm-up at full size (workspace allocation, first cluster launch)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
