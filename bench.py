@@ -617,7 +617,7 @@ def run_extras(proc, K, D, torch, dev, world=1, rank=0, dist=None):
              "resident_bytes_per_gpu": int(frames.numel()) * 2,
              "what": "BASELINE config 5: 4096 synthetic 1080p frames resident in HBM, contiguous frame ranges per GPU "
                      "(frame_shards), kmg_dev_reduce_batch: one cluster launch + one remap launch for the rank's frames"}
-    hn = 96
+    hn = 256
     hin = K.pinned_empty((hn, 1080, 1920, 4))
     hin[...] = frames[:hn].cpu().numpy()
     hout = K.pinned_empty((hn, 1080, 1920, 4))

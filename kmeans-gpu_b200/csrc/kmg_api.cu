@@ -193,6 +193,30 @@ struct Buf {
   }
 };
 
+// Page-locked host staging (small results that must not turn an async read-back into a blocking one)
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return KMG_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      return fail(KMG_ERR_OOM, "cudaMallocHost(%zu bytes) failed", bytes);
+    }
+    cap = bytes;
+    return KMG_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 struct Workspace {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // created on first use: uploads that overlap kernels on `stream`
@@ -201,8 +225,10 @@ struct Workspace {
   std::vector<cudaEvent_t> band_out;   // remap of a band finished (pipelined reduce)
   cudaEvent_t palette_ready = nullptr;
   Buf in, out, small, work, dmin, blob;
+  HostBuf stage;                // per-frame palettes and pass counts of a batch on their way to the caller
   JobState* h_state = nullptr;  // pinned
   void release() {
+    stage.release();
     for (cudaEvent_t e : band_done) cudaEventDestroy(e);
     band_done.clear();
     for (cudaEvent_t e : band_out) cudaEventDestroy(e);
@@ -1977,6 +2003,18 @@ extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_fr
   }
   auto run = [&]() -> int {
     const size_t stride = batch_blob_stride(k);
+    // The per-frame palettes and pass counts are staged in page-locked memory: read straight into
+    // the caller's (usually pageable) arrays, each chunk's read-back would block the host until
+    // the chunk's kernels had finished, and the next upload could not be queued behind them.
+    const size_t cent_bytes = centroids_out ? (size_t)n_frames * k * 16 : 0;
+    const size_t pass_bytes = passes_out ? (size_t)n_frames * 4 : 0;
+    float* h_cent = nullptr;
+    uint32_t* h_pass = nullptr;
+    if (cent_bytes + pass_bytes) {
+      TRY(wss[0]->stage.ensure(cent_bytes + pass_bytes));
+      if (cent_bytes) h_cent = (float*)wss[0]->stage.p;
+      if (pass_bytes) h_pass = (uint32_t*)((char*)wss[0]->stage.p + cent_bytes);
+    }
     for (uint32_t c = 0; c < n_chunks; ++c) {
       Workspace* ws = wss[c % n_ws];
       const uint32_t f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
@@ -1989,11 +2027,13 @@ extern "C" int kmg_reduce_batch(kmg_ctx* ctx, const uint8_t* rgba, uint32_t n_fr
       cudaStream_t s = ws->stream;
       CU(cudaMemcpyAsync(ws->in.p, rgba + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, s));
       TRY(reduce_batch_fused(ctx, cplan, (const uint8_t*)ws->in.p, nf, w, h, iw, ih, k, cs, mode, o, (uint8_t*)ws->out.p,
-                             ws->blob.p, ws->work.p, centroids_out ? centroids_out + (size_t)f0 * k * 4 : nullptr,
-                             passes_out ? passes_out + f0 : nullptr, s));
+                             ws->blob.p, ws->work.p, h_cent ? h_cent + (size_t)f0 * k * 4 : nullptr,
+                             h_pass ? h_pass + f0 : nullptr, s));
       CU(cudaMemcpyAsync(out_rgba + (size_t)f0 * frame_bytes, ws->out.p, (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, s));
     }
     for (uint32_t i = 0; i < n_ws; ++i) CU(cudaStreamSynchronize(wss[i]->stream));
+    if (h_cent) memcpy(centroids_out, h_cent, cent_bytes);
+    if (h_pass) memcpy(passes_out, h_pass, pass_bytes);
     return KMG_OK;
   };
   if (rc == KMG_OK) rc = run();
