@@ -83,11 +83,11 @@ __device__ __forceinline__ bool init_exchange(const PeerXchg& X, unsigned int k,
   return true;
 }
 
-constexpr unsigned int LAZY_QCAP = 768;  // candidate indices a warp can hold (a step adds at most 256)
+constexpr unsigned int LAZY_QCAP = 1280;  // candidate indices a warp can hold (a step adds at most 256, four steps per check)
 
 // PICK 1: single GPU.  PICK 2: sharded image, peer mailboxes.
 // Dynamic shared memory: float4 cent[k] (x, y, z, chroma) + uint32 queue[8 warps][LAZY_QCAP].
-// Every warp sweeps its own 256-pixel steps (one 128-bit load of eight 16-bit bounds per lane, two
+// Every warp sweeps its own 256-pixel steps (one 128-bit load of eight 16-bit bounds per lane, four
 // steps in flight), collects the candidates in its own queue and refreshes them 32 at a time when the
 // queue fills up or the sweep ends — no block barrier inside a sweep.
 template <int PICK>
@@ -103,12 +103,17 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
   const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   unsigned int* s_queue = reinterpret_cast<unsigned int*>(smem_raw + (size_t)k * 16) + warp * LAZY_QCAP;
   __shared__ unsigned int s_nc, s_fault, s_resolved;
+  __shared__ unsigned int s_qn[8];  // entries reserved in each warp's queue
   __shared__ unsigned long long s_key[8];
   if (tid == 0) s_nc = 0;
+  if (tid < 8) s_qn[tid] = 0;
   const unsigned long long steps = (n + 255) / 256;  // warp steps of 32 lanes x 8 pixels
   const unsigned long long gwarp = (unsigned long long)blockIdx.x * 8 + warp, gwarps = (unsigned long long)gridDim.x * 8;
   unsigned long long refreshed = 0, folds = 0, exact = 0;
   unsigned int fails = 0;  // block 0, thread 0: unresolved sweeps of the current round
+#ifdef KMG_LAZY_PROF
+  long long t_drain = 0, t_sync = 0, t_all = -clock64(), t_tmp;
+#endif
 
   // rounds 1 .. j0-1 were full sweeps (k_init_round with bounds): centroids 0 .. j0-1 exist, every
   // minimum is exact w.r.t. centroids 0 .. j0-2
@@ -132,6 +137,9 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
       // refresh the queued candidates, 32 at a time: fold centroids fold .. j-1 into the minimum
       auto drain = [&]() {
         __syncwarp();
+#ifdef KMG_LAZY_PROF
+        t_drain -= clock64();
+#endif
         for (unsigned int q = lane; q < qn; q += 32) {
           const unsigned long long p = s_queue[q];
           const float4 v = work[p];
@@ -168,63 +176,89 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
               ((unsigned long long)__float_as_uint(d) << 32) | (((pixel_offset + p) & 0xffffffffull) ^ 15ull);
           best = key > best ? key : best;
         }
+        if (lane == 0) s_qn[warp] = 0;
         __syncwarp();
+#ifdef KMG_LAZY_PROF
+        t_drain += clock64();
+#endif
         qn = 0;
       };
 
       {
-        // sweep of the bounds: lane l of a step holds pixels step * 256 + 8 l .. + 7
-        auto load8 = [&](unsigned long long step, unsigned int (&u)[8]) {
-          const unsigned long long p0 = step * 256 + (unsigned long long)lane * 8;
-          if (step < steps && p0 + 8 <= n) {
-            const uint4 q = __ldcg(reinterpret_cast<const uint4*>(ub + p0));
-            u[0] = q.x & 0xffffu; u[1] = q.x >> 16; u[2] = q.y & 0xffffu; u[3] = q.y >> 16;
-            u[4] = q.z & 0xffffu; u[5] = q.z >> 16; u[6] = q.w & 0xffffu; u[7] = q.w >> 16;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) u[e] = (step < steps && p0 + e < n) ? (unsigned int)__ldcg(ub + p0 + e) : 0xffffffffu;  // past the end
+        // sweep of the bounds: lane l of a step holds pixels step * 256 + 8 l .. + 7, two 16-bit bounds
+        // per word.  The upper bound of a word is tested in place (word >= tau << 16 <=> upper half >= tau,
+        // and the largest skipped word carries the largest skipped upper half), the lower one shifted up.
+        const unsigned int tau_hi = tau16 << 16;
+        unsigned int nc_hi = 0, nc_lo = 0, skipped = 0;
+        // candidates of one step into the warp's queue: the lanes that hold some reserve their places
+        // with one shared-memory add (the order inside the queue does not matter)
+        auto push = [&](unsigned long long step, unsigned int mine) {
+          qn += __reduce_add_sync(0xffffffffu, __popc(mine));
+          if (mine) {
+            unsigned int at = atomicAdd(&s_qn[warp], (unsigned int)__popc(mine));
+            const unsigned int p0 = (unsigned int)(step * 256 + (unsigned long long)lane * 8);
+            do {
+              s_queue[at++] = p0 + (unsigned int)__ffs((int)mine) - 1u;
+              mine &= mine - 1u;
+            } while (mine);
           }
         };
-        auto take = [&](unsigned long long step, const unsigned int (&u)[8]) {
+        auto take = [&](unsigned long long step, const uint4& q) {
+          const unsigned int w[4] = {q.x, q.y, q.z, q.w};
           unsigned int mine = 0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (u[e] == 0xffffffffu) continue;
-            if (u[e] >= tau16)
-              mine |= 1u << e;
+          for (int e = 0; e < 4; ++e) {
+            const unsigned int lo = w[e] << 16;
+            if (w[e] >= tau_hi)
+              mine |= 2u << (2 * e);
             else
-              ncmax = max(ncmax, u[e] + 1u);
+              nc_hi = max(nc_hi, w[e]);
+            if (lo >= tau_hi)
+              mine |= 1u << (2 * e);
+            else
+              nc_lo = max(nc_lo, lo);
           }
-          // warp-level compaction: exclusive prefix of the lanes' candidate counts
-          const unsigned int c = __popc(mine);
-          unsigned int incl = c;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
-          }
-          const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-          if (total) {
-            unsigned int at = qn + incl - c;
-            const unsigned int p0 = (unsigned int)(step * 256 + (unsigned long long)lane * 8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (mine & (1u << e)) s_queue[at++] = p0 + e;
-            qn += total;
-            if (qn > LAZY_QCAP - 256) drain();
-          }
+          skipped |= mine ^ 0xffu;
+          push(step, mine);
         };
-        unsigned int ua[8], ubb[8];
+        const unsigned long long full = n / 256;  // steps with all 256 pixels
+        auto load = [&](unsigned long long step) {
+          return step < full ? __ldcg(reinterpret_cast<const uint4*>(ub + step * 256 + (unsigned long long)lane * 8))
+                             : make_uint4(0u, 0u, 0u, 0u);
+        };
         unsigned long long step = gwarp;
-        load8(step, ua);
-        for (; step < steps; step += 2 * gwarps) {
-          load8(step + gwarps, ubb);
-          take(step, ua);
-          load8(step + 2 * gwarps, ua);
-          if (step + gwarps < steps) take(step + gwarps, ubb);
+        uint4 q0 = load(step), q1 = load(step + gwarps), q2 = load(step + 2 * gwarps), q3 = load(step + 3 * gwarps);
+        for (; step < full; step += 4 * gwarps) {  // four loads in flight per lane
+          take(step, q0);
+          q0 = load(step + 4 * gwarps);
+          if (step + gwarps < full) take(step + gwarps, q1);
+          q1 = load(step + 5 * gwarps);
+          if (step + 2 * gwarps < full) take(step + 2 * gwarps, q2);
+          q2 = load(step + 6 * gwarps);
+          if (step + 3 * gwarps < full) take(step + 3 * gwarps, q3);
+          q3 = load(step + 7 * gwarps);
+          if (qn > LAZY_QCAP - 1024) drain();
+        }
+        if (full < steps && full % gwarps == gwarp) {  // the ragged last step, pixel by pixel
+          const unsigned long long p0 = full * 256 + (unsigned long long)lane * 8;
+          unsigned int mine = 0;
+          for (unsigned int e = 0; e < 8 && p0 + e < n; ++e) {
+            const unsigned int u = __ldcg(ub + p0 + e);
+            if (u >= tau16) {
+              mine |= 1u << e;
+            } else {
+              nc_lo = max(nc_lo, u << 16);
+              skipped = 1;
+            }
+          }
+          push(full, mine);
         }
         drain();
+        ncmax = skipped ? (max(nc_hi, nc_lo) >> 16) + 1u : 0u;
       }
+#ifdef KMG_LAZY_PROF
+      t_sync -= clock64();
+#endif
       // warp -> block -> grid
       best = warp_max_u64(best);
       ncmax = __reduce_max_sync(0xffffffffu, ncmax);
@@ -301,9 +335,17 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
       }
       __threadfence();
       grid.sync();
+#ifdef KMG_LAZY_PROF
+      t_sync += clock64();
+#endif
       if (__ldcg(&st->init_done_round) == j) break;
     }
   }
+#ifdef KMG_LAZY_PROF
+  t_all += clock64();
+  refreshed = (unsigned long long)t_drain; folds = (unsigned long long)t_sync; exact = (unsigned long long)t_all;
+  if (lane) { refreshed = 0; folds = 0; exact = 0; }
+#endif
   refreshed = (unsigned long long)warp_sum_i64((long long)refreshed);
   folds = (unsigned long long)warp_sum_i64((long long)folds);
   if (lane == 0 && refreshed) {
