@@ -18,6 +18,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 rep, kern, fname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+import os
+INNER = bool(os.environ.get("NCU_INNER"))  # charge to the innermost location in the file instead (inside lambdas)
 
 tmp = Path(tempfile.mkdtemp())
 subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "kmeans-gpu_b200" / "lib" / "libkmeans_gpu.so")], cwd=tmp,
@@ -44,7 +46,7 @@ for l in sass[start + 1:]:
     m = ins_re.search(l)
     if m:
         mine = [c for c in chain if c[0].endswith(fname)]
-        off2line[int(m.group(1), 16)] = mine[-1][1] if mine else -1
+        off2line[int(m.group(1), 16)] = (mine[0 if INNER else -1][1]) if mine else -1
         after_ins = True
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
