@@ -111,9 +111,6 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
   const unsigned long long gwarp = (unsigned long long)blockIdx.x * 8 + warp, gwarps = (unsigned long long)gridDim.x * 8;
   unsigned long long refreshed = 0, folds = 0, exact = 0;
   unsigned int fails = 0;  // block 0, thread 0: unresolved sweeps of the current round
-#ifdef KMG_LAZY_PROF
-  long long t_drain = 0, t_sync = 0, t_all = -clock64(), t_tmp;
-#endif
 
   // rounds 1 .. j0-1 were full sweeps (k_init_round with bounds): centroids 0 .. j0-1 exist, every
   // minimum is exact w.r.t. centroids 0 .. j0-2
@@ -137,9 +134,6 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
       // refresh the queued candidates, 32 at a time: fold centroids fold .. j-1 into the minimum
       auto drain = [&]() {
         __syncwarp();
-#ifdef KMG_LAZY_PROF
-        t_drain -= clock64();
-#endif
         for (unsigned int q = lane; q < qn; q += 32) {
           const unsigned long long p = s_queue[q];
           const float4 v = work[p];
@@ -178,9 +172,6 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
         }
         if (lane == 0) s_qn[warp] = 0;
         __syncwarp();
-#ifdef KMG_LAZY_PROF
-        t_drain += clock64();
-#endif
         qn = 0;
       };
 
@@ -256,9 +247,6 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
         drain();
         ncmax = skipped ? (max(nc_hi, nc_lo) >> 16) + 1u : 0u;
       }
-#ifdef KMG_LAZY_PROF
-      t_sync -= clock64();
-#endif
       // warp -> block -> grid
       best = warp_max_u64(best);
       ncmax = __reduce_max_sync(0xffffffffu, ncmax);
@@ -335,17 +323,9 @@ __global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* _
       }
       __threadfence();
       grid.sync();
-#ifdef KMG_LAZY_PROF
-      t_sync += clock64();
-#endif
       if (__ldcg(&st->init_done_round) == j) break;
     }
   }
-#ifdef KMG_LAZY_PROF
-  t_all += clock64();
-  refreshed = (unsigned long long)t_drain; folds = (unsigned long long)t_sync; exact = (unsigned long long)t_all;
-  if (lane) { refreshed = 0; folds = 0; exact = 0; }
-#endif
   refreshed = (unsigned long long)warp_sum_i64((long long)refreshed);
   folds = (unsigned long long)warp_sum_i64((long long)folds);
   if (lane == 0 && refreshed) {
