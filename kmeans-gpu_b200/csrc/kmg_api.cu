@@ -777,7 +777,7 @@ static int launch_prepare(kmg_job* j, bool palette, cudaStream_t s) {
   return KMG_OK;
 }
 
-static constexpr unsigned int MBOX_XCAP = MAX_K * 4;  // int64 slots per (parity, rank)
+static constexpr unsigned int MBOX_XCAP = MAX_K * 8;  // 8-byte words per (parity, rank): k x 4 values, two words each
 static constexpr size_t MBOX_DATA_BYTES = (size_t)2 * MAX_PEERS * MBOX_XCAP * 8;
 static constexpr size_t MBOX_BYTES = MBOX_DATA_BYTES + (size_t)2 * MAX_PEERS * 4;
 

@@ -40,49 +40,6 @@ constexpr float LAZY_RHO = 0.98f;
 // smallest 16-bit value u with float(u << 16) >= d (d >= 0, finite)
 __device__ __forceinline__ unsigned int up16(float d) { return (__float_as_uint(d) + 0xffffu) >> 16; }
 
-// The mailbox exchange of one init round between the GPUs that share an image (see k_init_round<., 2>):
-// thread 0 holds this rank's (key, global pixel or ~0, colour) and returns the winner's.  All threads
-// of the block call it.
-__device__ __forceinline__ bool init_exchange(const PeerXchg& X, unsigned int k, unsigned int j, unsigned long long& key,
-                                              unsigned long long pix, float4& col, unsigned int* s_fault) {
-  const unsigned int par = (k - j) & 1u;
-  const unsigned int seq = X.seq_base - j;
-  if (threadIdx.x == 0) {
-    *s_fault = 0;
-    const size_t slot = ((size_t)par * MAX_PEERS + X.rank) * X.xcap;
-    for (unsigned int r = 0; r < X.n_ranks; ++r) {
-      longlong2* dst = reinterpret_cast<longlong2*>(X.mbox[r] + slot);
-      dst[0] = make_longlong2((long long)key, (long long)pix);
-      dst[1] = make_longlong2((long long)(((unsigned long long)__float_as_uint(col.y) << 32) | __float_as_uint(col.x)),
-                              (long long)__float_as_uint(col.z));
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x < X.n_ranks) xchg_flags(X, par, seq, threadIdx.x, s_fault);
-  __syncthreads();
-  if (*s_fault) return false;
-  if (threadIdx.x == 0) {
-    unsigned long long kmax = 0ull;
-    for (unsigned int r = 0; r < X.n_ranks; ++r) {
-      const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap;
-      const unsigned long long kr = (unsigned long long)a[0];
-      kmax = kr > kmax ? kr : kmax;
-    }
-    const unsigned long long want = key_to_pixel(kmax);
-    for (unsigned int r = 0; r < X.n_ranks; ++r) {
-      const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap;
-      if ((unsigned long long)a[1] == want) {
-        const unsigned long long la = (unsigned long long)a[2];
-        col = make_float4(__uint_as_float((unsigned int)la), __uint_as_float((unsigned int)(la >> 32)),
-                          __uint_as_float((unsigned int)(unsigned long long)a[3]), 1.0f);
-      }
-    }
-    key = kmax;
-  }
-  return true;
-}
-
 constexpr unsigned int LAZY_QCAP = 1280;  // candidate indices a warp can hold (a step adds at most 256, four steps per check)
 
 // PICK 1: single GPU.  PICK 2: sharded image, peer mailboxes.
@@ -90,8 +47,10 @@ constexpr unsigned int LAZY_QCAP = 1280;  // candidate indices a warp can hold (
 // Every warp sweeps its own 256-pixel steps (one 128-bit load of eight 16-bit bounds per lane, four
 // steps in flight), collects the candidates in its own queue and refreshes them 32 at a time when the
 // queue fills up or the sweep ends — no block barrier inside a sweep.
+// (the sharded variant carries the exchange code: three blocks per SM keep its sweep free of spills,
+// measured faster on 2 GPUs; the single-GPU variant is faster with four)
 template <int PICK>
-__global__ void __launch_bounds__(256, 4) k_init_lazy(JobPtrs J, const float4* __restrict__ work, float* __restrict__ dmin,
+__global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J, const float4* __restrict__ work, float* __restrict__ dmin,
                                                    unsigned short* __restrict__ ub, unsigned short* __restrict__ fold,
                                                    unsigned long long n, unsigned long long pixel_offset, PeerXchg X,
                                                    unsigned int j0) {

@@ -72,53 +72,94 @@ __host__ __device__ inline unsigned int pad32(unsigned int k) { return (k + 31u)
 
 // Multi-GPU pixel sharding without a separate collective: the last block of a Lloyd pass on every
 // GPU stores its k x 4 partial sums straight into every peer's mailbox (peer-mapped memory, the
-// stores travel over NVLink / NVSwitch), raises a flag there, waits for the peers' flags in its
-// own mailbox and finalises — reduction and pass are one kernel.  Mailbox of a GPU:
-//   mbox  [2 parities][MAX_PEERS ranks][xcap] int64     flags [2 parities][MAX_PEERS ranks] u32
+// stores travel over NVLink / NVSwitch), waits for the peers' sums in its own mailbox and finalises
+// — reduction and pass are one kernel.  Every 64-bit value travels as two 8-byte words
+// {32 payload bits, sequence number}: an aligned 8-byte store arrives whole, so a word that shows the
+// expected sequence number is valid by itself — no fence, no separate flag, one NVLink flight.
+// Mailbox of a GPU:
+//   mbox  [2 parities][MAX_PEERS ranks][xcap] words     flags [2 parities][MAX_PEERS ranks] u32 (poison only)
 constexpr unsigned int MAX_PEERS = 8;
 struct PeerXchg {
   unsigned int n_ranks;  // 0: not in use
   unsigned int rank;
-  unsigned int xcap;     // int64 slots per (parity, rank), >= 4 k
-  unsigned int seq_base; // flags carry seq_base + pass number + 1 (distinct per job)
+  unsigned int xcap;     // 8-byte words per (parity, rank), >= 8 k
+  unsigned int seq_base; // words carry seq_base + pass number + 1 (distinct per job)
   long long* mbox[MAX_PEERS];      // rank r's mailbox as mapped on this GPU
   unsigned int* flags[MAX_PEERS];
 };
 constexpr unsigned int PASS_FAULT = 0xffffffffu;  // JobState::conv when a peer did not answer
 constexpr unsigned int XCHG_POISON = 0xdeadbeefu; // flag value a rank that gave up leaves in every mailbox
 
-// Flag half of a mailbox exchange; threads 0 .. n_ranks-1 of the block call it after the data has
-// been stored to the peers and fenced.  Thread r raises this rank's flag in peer r's mailbox and waits
-// for peer r's flag in its own.  A rank that waits longer than 4 s (a peer never launched the
-// matching kernel) gives up — and poisons its flag in EVERY mailbox, both parities, so that the peers
-// fault in their current or next exchange as well instead of finishing the pass and running on with
-// centroids this rank never got: all ranks of a job fail together (KMG_ERR_NCCL on each), and the
-// communicator stays poisoned until kmg_comm_destroy / kmg_comm_init.
-__device__ __forceinline__ void xchg_flags(const PeerXchg& X, unsigned int par, unsigned int seq, unsigned int r,
-                                           unsigned int* s_fault) {
-  volatile unsigned int* theirs = X.flags[r] + par * MAX_PEERS + X.rank;
-  if (*theirs != XCHG_POISON) *theirs = seq;
-  volatile unsigned int* mine = X.flags[X.rank] + par * MAX_PEERS + r;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    const unsigned int v = *mine;
-    if (v == seq) break;
-    bool fault = v == XCHG_POISON;
-    if (!fault) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      fault = t1 - t0 > 4000000000ull;
-    }
-    if (fault) {
-      *s_fault = 1;
-      for (unsigned int q = 0; q < X.n_ranks; ++q) {
-        *(volatile unsigned int*)(X.flags[q] + X.rank) = XCHG_POISON;
-        *(volatile unsigned int*)(X.flags[q] + MAX_PEERS + X.rank) = XCHG_POISON;
-      }
-      break;
+// Word w of this rank's stretch (pass parity par) in peer r's mailbox / of rank r's stretch in this GPU's own.
+__device__ __forceinline__ volatile unsigned long long* xchg_out(const PeerXchg& X, unsigned int par, unsigned int r,
+                                                                 size_t w) {
+  return reinterpret_cast<volatile unsigned long long*>(X.mbox[r]) + ((size_t)par * MAX_PEERS + X.rank) * X.xcap + w;
+}
+__device__ __forceinline__ const volatile unsigned long long* xchg_in(const PeerXchg& X, unsigned int par, unsigned int r,
+                                                                       size_t w) {
+  return reinterpret_cast<const volatile unsigned long long*>(X.mbox[X.rank]) + ((size_t)par * MAX_PEERS + r) * X.xcap + w;
+}
+// 64-bit value number i of this rank's stretch, to peer r: words 2 i and 2 i + 1
+__device__ __forceinline__ void xchg_post64(const PeerXchg& X, unsigned int par, unsigned int seq, unsigned int r, size_t i,
+                                            unsigned long long v) {
+  volatile unsigned long long* d = xchg_out(X, par, r, 2 * i);
+  d[0] = ((unsigned long long)seq << 32) | (v & 0xffffffffull);
+  d[1] = ((unsigned long long)seq << 32) | (v >> 32);
+}
+// A rank that waits longer than 4 s for a word (a peer never launched the matching kernel) gives up
+// — and poisons its flag in EVERY mailbox, both parities, so that the peers fault in their current or
+// next exchange as well instead of finishing the pass and running on with centroids this rank never
+// got: all ranks of a job fail together (KMG_ERR_NCCL on each), and the communicator stays poisoned
+// until kmg_comm_destroy / kmg_comm_init.
+__device__ __forceinline__ bool xchg_gave_up(const PeerXchg& X, unsigned int par, unsigned int r, unsigned long long t0,
+                                          unsigned int* s_fault) {
+  bool fault = *(volatile unsigned int*)(X.flags[X.rank] + par * MAX_PEERS + r) == XCHG_POISON;
+  if (!fault) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    fault = t1 - t0 > 4000000000ull;
+  }
+  if (fault) {
+    *s_fault = 1;
+    for (unsigned int q = 0; q < X.n_ranks; ++q) {
+      *(volatile unsigned int*)(X.flags[q] + X.rank) = XCHG_POISON;
+      *(volatile unsigned int*)(X.flags[q] + MAX_PEERS + X.rank) = XCHG_POISON;
     }
   }
-  __threadfence_system();
+  return fault;
+}
+// 64-bit value number i of every rank's stretch, summed in rank order (ADD) or handed back one by one.
+// All 2 n words are requested before the first one is looked at; stragglers are polled again.
+template <typename F>
+__device__ __forceinline__ void xchg_gather64(const PeerXchg& X, unsigned int par, unsigned int seq, size_t i,
+                                              unsigned int* s_fault, F&& use) {
+  unsigned long long t0 = 0;
+#pragma unroll 1
+  for (unsigned int r0 = 0; r0 < X.n_ranks; r0 += 4) {
+    unsigned long long lo[4], hi[4];
+#pragma unroll
+    for (unsigned int q = 0; q < 4; ++q) {
+      if (r0 + q < X.n_ranks) {
+        const volatile unsigned long long* a = xchg_in(X, par, r0 + q, 2 * i);
+        lo[q] = a[0];
+        hi[q] = a[1];
+      }
+    }
+#pragma unroll
+    for (unsigned int q = 0; q < 4; ++q) {
+      if (r0 + q < X.n_ranks) {
+        const volatile unsigned long long* a = xchg_in(X, par, r0 + q, 2 * i);
+        unsigned int spins = 0;
+        while ((unsigned int)(lo[q] >> 32) != seq || (unsigned int)(hi[q] >> 32) != seq) {
+          if (t0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          if ((spins++ & 255u) == 0 && xchg_gave_up(X, par, r0 + q, t0, s_fault)) break;
+          lo[q] = a[0];
+          hi[q] = a[1];
+        }
+        use(r0 + q, (lo[q] & 0xffffffffull) | (hi[q] << 32));
+      }
+    }
+  }
 }
 
 // The job blob of frame f in a batch: every pointer shifted by f * blob_stride bytes.
@@ -795,6 +836,47 @@ __device__ __forceinline__ unsigned long long key_to_pixel(unsigned long long ke
   return (key >> 32) == 0ull ? 0ull : ((key & 0xffffffffull) ^ 15ull);
 }
 
+// The mailbox exchange of one init round between the GPUs that share an image: thread 0 holds this
+// rank's (key, global pixel or ~0, colour) and gets the winner's.  All threads of the block call it
+// (at least 32 of them).  Four 64-bit values per rank: thread t posts value t & 3 to rank t >> 2,
+// threads 0-3 gather one value of every rank each.
+__device__ __forceinline__ bool init_exchange(const PeerXchg& X, unsigned int k, unsigned int j, unsigned long long& key,
+                                              unsigned long long pix, float4& col, unsigned int* s_fault) {
+  __shared__ unsigned long long s_mine[4];
+  __shared__ unsigned long long s_all[MAX_PEERS][4];
+  const unsigned int par = (k - j) & 1u;
+  const unsigned int seq = X.seq_base - j;
+  const unsigned int t = threadIdx.x;
+  if (t == 0) {
+    *s_fault = 0;
+    s_mine[0] = key;
+    s_mine[1] = pix;
+    s_mine[2] = ((unsigned long long)__float_as_uint(col.y) << 32) | __float_as_uint(col.x);
+    s_mine[3] = __float_as_uint(col.z);
+  }
+  __syncthreads();
+  if (t < 4 * X.n_ranks) xchg_post64(X, par, seq, t >> 2, t & 3u, s_mine[t & 3u]);
+  if (t < 4) xchg_gather64(X, par, seq, t, s_fault, [&](unsigned int r, unsigned long long v) { s_all[r][t] = v; });
+  __syncthreads();
+  if (*s_fault) return false;
+  if (t == 0) {
+    // largest key over the ranks (keys of different shards never tie: they embed the global pixel
+    // index; all-zero maxima resolve to global pixel 0), colour from the rank that holds it
+    unsigned long long kmax = 0ull;
+    for (unsigned int r = 0; r < X.n_ranks; ++r) kmax = s_all[r][0] > kmax ? s_all[r][0] : kmax;
+    const unsigned long long want = key_to_pixel(kmax);
+    for (unsigned int r = 0; r < X.n_ranks; ++r) {
+      if (s_all[r][1] == want) {
+        const unsigned long long la = s_all[r][2];
+        col = make_float4(__uint_as_float((unsigned int)la), __uint_as_float((unsigned int)(la >> 32)),
+                          __uint_as_float((unsigned int)s_all[r][3]), 1.0f);
+      }
+    }
+    key = kmax;
+  }
+  return true;
+}
+
 // rgba != NULL: the work plane does not exist yet (the first init round will write it, fused with the
 // conversion): the seed pixel is converted here.
 __global__ void k_init_seed(JobPtrs J, const float4* __restrict__ work, unsigned long long seed_local,
@@ -929,46 +1011,9 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
     }
   }
   if (PICK == 2) {
-    const unsigned int k = J.st->k;
-    const unsigned int par = (k - j) & 1u;
-    const unsigned int seq = X.seq_base - j;
-    if (threadIdx.x == 0) {
-      const size_t slot = ((size_t)par * MAX_PEERS + X.rank) * X.xcap;
-      for (unsigned int r = 0; r < X.n_ranks; ++r) {
-        longlong2* dst = reinterpret_cast<longlong2*>(X.mbox[r] + slot);
-        dst[0] = make_longlong2((long long)key, (long long)pix);
-        dst[1] = make_longlong2((long long)(((unsigned long long)__float_as_uint(col.y) << 32) | __float_as_uint(col.x)),
-                                (long long)__float_as_uint(col.z));
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-    if (threadIdx.x < X.n_ranks) xchg_flags(X, par, seq, threadIdx.x, &s_fault);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_fault) {
-        J.st->conv = PASS_FAULT;
-        J.st->done = 1;
-      } else {
-        // largest key over the ranks (keys of different shards never tie: they embed the global
-        // pixel index; all-zero maxima resolve to global pixel 0), colour from the rank that holds it
-        unsigned long long kmax = 0ull;
-        for (unsigned int r = 0; r < X.n_ranks; ++r) {
-          const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap;
-          const unsigned long long kr = (unsigned long long)a[0];
-          kmax = kr > kmax ? kr : kmax;
-        }
-        const unsigned long long want = key_to_pixel(kmax);
-        for (unsigned int r = 0; r < X.n_ranks; ++r) {
-          const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap;
-          if ((unsigned long long)a[1] == want) {
-            const unsigned long long la = (unsigned long long)a[2];
-            col = make_float4(__uint_as_float((unsigned int)la), __uint_as_float((unsigned int)(la >> 32)),
-                              __uint_as_float((unsigned int)(unsigned long long)a[3]), 1.0f);
-          }
-        }
-        key = kmax;
-      }
+    if (!init_exchange(X, J.st->k, j, key, pix, col, &s_fault) && threadIdx.x == 0) {
+      J.st->conv = PASS_FAULT;
+      J.st->done = 1;
     }
   }
   if (threadIdx.x == 0) {
@@ -1033,16 +1078,17 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, int mode, const
           a[q] = 0;
         }
       }
-      const size_t slot = ((size_t)par * MAX_PEERS + X.rank) * X.xcap + (size_t)c * 4;
       for (unsigned int r = 0; r < X.n_ranks; ++r) {
-        longlong2* dst = reinterpret_cast<longlong2*>(X.mbox[r] + slot);
-        dst[0] = make_longlong2(s[0], s[1]);
-        dst[1] = make_longlong2(s[2], s[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xchg_post64(X, par, seq, r, (size_t)c * 4 + q, (unsigned long long)s[q]);
       }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < X.n_ranks) xchg_flags(X, par, seq, tid, &s_fault);
+    // gather: one thread per (centroid, component), the ranks' values added in rank order on every GPU
+    for (unsigned int i = tid; i < 4 * k; i += THREADS) {
+      long long sum = 0;
+      xchg_gather64(X, par, seq, i, &s_fault, [&](unsigned int, unsigned long long v) { sum += (long long)v; });
+      J.last[i] = sum;
+    }
     __syncthreads();
     if (s_fault) {
       if (tid == 0) {
@@ -1057,11 +1103,8 @@ __device__ void finalize_pass(const JobPtrs& J, int color_space, int mode, const
   for (unsigned int c = tid; c < k; c += THREADS) {
     long long s[4] = {0, 0, 0, 0};
     if (mode == 2) {
-      for (unsigned int r = 0; r < X.n_ranks; ++r) {  // fixed rank order on every GPU
-        const volatile long long* a = X.mbox[X.rank] + ((size_t)par * MAX_PEERS + r) * X.xcap + (size_t)c * 4;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) s[q] += a[q];
-      }
+      for (int q = 0; q < 4; ++q) s[q] = __ldcg(J.last + (size_t)c * 4 + q);
     } else {
       for (unsigned int copy = 0; copy < J.acc_copies; ++copy) {
         long long* a = J.acc + ((size_t)copy * k + c) * 4;
