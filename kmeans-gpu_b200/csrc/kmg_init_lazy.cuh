@@ -66,9 +66,10 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
   __shared__ unsigned long long s_key[8];
   if (tid == 0) s_nc = 0;
   if (tid < 8) s_qn[tid] = 0;
-  const unsigned long long steps = (n + 255) / 256;  // warp steps of 32 lanes x 8 pixels
-  const unsigned long long gwarp = (unsigned long long)blockIdx.x * 8 + warp, gwarps = (unsigned long long)gridDim.x * 8;
-  unsigned long long refreshed = 0, folds = 0, exact = 0;
+  // n < 2^32 (validate_dims): step numbers and the per-thread statistics fit 32 bits
+  const unsigned int steps = (unsigned int)((n + 255) / 256);  // warp steps of 32 lanes x 8 pixels
+  const unsigned int gwarp = blockIdx.x * 8 + warp, gwarps = gridDim.x * 8;
+  unsigned int refreshed = 0, folds = 0, exact = 0;
   unsigned int fails = 0;  // block 0, thread 0: unresolved sweeps of the current round
 
   // rounds 1 .. j0-1 were full sweeps (k_init_round with bounds): centroids 0 .. j0-1 exist, every
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
       auto drain = [&]() {
         __syncwarp();
         for (unsigned int q = lane; q < qn; q += 32) {
-          const unsigned long long p = s_queue[q];
+          const unsigned int p = s_queue[q];
           const float4 v = work[p];
           float d = __ldcg(dmin + p);
           const unsigned int f = max((unsigned int)__ldcg(fold + p), j0 - 1u);  // rounds < j0 were full sweeps: centroids 0 .. j0-2 are in
@@ -142,18 +143,18 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
         unsigned int nc_hi = 0, nc_lo = 0, skipped = 0;
         // candidates of one step into the warp's queue: the lanes that hold some reserve their places
         // with one shared-memory add (the order inside the queue does not matter)
-        auto push = [&](unsigned long long step, unsigned int mine) {
+        auto push = [&](unsigned int step, unsigned int mine) {
           qn += __reduce_add_sync(0xffffffffu, __popc(mine));
           if (mine) {
             unsigned int at = atomicAdd(&s_qn[warp], (unsigned int)__popc(mine));
-            const unsigned int p0 = (unsigned int)(step * 256 + (unsigned long long)lane * 8);
+            const unsigned int p0 = step * 256 + lane * 8;
             do {
               s_queue[at++] = p0 + (unsigned int)__ffs((int)mine) - 1u;
               mine &= mine - 1u;
             } while (mine);
           }
         };
-        auto take = [&](unsigned long long step, const uint4& q) {
+        auto take = [&](unsigned int step, const uint4& q) {
           const unsigned int w[4] = {q.x, q.y, q.z, q.w};
           unsigned int mine = 0;
 #pragma unroll
@@ -171,12 +172,12 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
           skipped |= mine ^ 0xffu;
           push(step, mine);
         };
-        const unsigned long long full = n / 256;  // steps with all 256 pixels
-        auto load = [&](unsigned long long step) {
-          return step < full ? __ldcg(reinterpret_cast<const uint4*>(ub + step * 256 + (unsigned long long)lane * 8))
+        const unsigned int full = (unsigned int)(n / 256);  // steps with all 256 pixels
+        auto load = [&](unsigned int step) {
+          return step < full ? __ldcg(reinterpret_cast<const uint4*>(ub + (size_t)step * 256 + lane * 8))
                              : make_uint4(0u, 0u, 0u, 0u);
         };
-        unsigned long long step = gwarp;
+        unsigned int step = gwarp;
         uint4 q0 = load(step), q1 = load(step + gwarps), q2 = load(step + 2 * gwarps), q3 = load(step + 3 * gwarps);
         for (; step < full; step += 4 * gwarps) {  // four loads in flight per lane
           take(step, q0);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
           if (qn > LAZY_QCAP - 1024) drain();
         }
         if (full < steps && full % gwarps == gwarp) {  // the ragged last step, pixel by pixel
-          const unsigned long long p0 = full * 256 + (unsigned long long)lane * 8;
+          const unsigned long long p0 = (unsigned long long)full * 256 + lane * 8;
           unsigned int mine = 0;
           for (unsigned int e = 0; e < 8 && p0 + e < n; ++e) {
             const unsigned int u = __ldcg(ub + p0 + e);
@@ -285,14 +286,14 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
       if (__ldcg(&st->init_done_round) == j) break;
     }
   }
-  refreshed = (unsigned long long)warp_sum_i64((long long)refreshed);
-  folds = (unsigned long long)warp_sum_i64((long long)folds);
-  if (lane == 0 && refreshed) {
-    atomicAdd(&st->init_refreshed, refreshed);
-    atomicAdd(&st->init_folds, folds);
+  const unsigned long long refreshed_w = (unsigned long long)warp_sum_i64((long long)refreshed);
+  const unsigned long long folds_w = (unsigned long long)warp_sum_i64((long long)folds);
+  const unsigned long long exact_w = (unsigned long long)warp_sum_i64((long long)exact);
+  if (lane == 0 && refreshed_w) {
+    atomicAdd(&st->init_refreshed, refreshed_w);
+    atomicAdd(&st->init_folds, folds_w);
   }
-  exact = (unsigned long long)warp_sum_i64((long long)exact);
-  if (lane == 0 && exact) atomicAdd(&st->init_exact, exact);
+  if (lane == 0 && exact_w) atomicAdd(&st->init_exact, exact_w);
 }
 
 }  // namespace kmg
