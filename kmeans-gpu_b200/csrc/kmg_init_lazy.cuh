@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(256, PICK == 2 ? 3 : 4) k_init_lazy(JobPtrs J,
       }
       __threadfence();
       grid.sync();
+      // a peer is gone: every later round would wait 4 s for it again — all blocks leave together
+      if (PICK == 2 && __ldcg(&st->conv) == PASS_FAULT) return;
       if (__ldcg(&st->init_done_round) == j) break;
     }
   }

@@ -936,6 +936,8 @@ __global__ void __launch_bounds__(256) k_init_round(JobPtrs J, const float4* __r
     lut[threadIdx.x] = lut_g[threadIdx.x];
     __syncthreads();
   }
+  // a peer is gone (an earlier exchange of this job gave up): every later round would wait for it again
+  if (PICK == 2 && J.st->conv == PASS_FAULT) return;
   // centroid j-1 was resolved into J.cent[j-1] by the previous round (or k_init_seed for j == 1).
   const float4 c = J.cent[j - 1];
   const float cc = ex::chroma(c.y, c.z);
