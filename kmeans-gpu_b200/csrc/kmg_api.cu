@@ -1038,8 +1038,8 @@ static int job_init_impl(kmg_job* j, uint32_t* pick_index, float* pick_dist, cud
   const PeerXchg X = peer_xchg(ctx, j, fused);
   // All rounds in one cooperative launch that only refreshes the pixels that can still win
   // (kmg_init_lazy.cuh); KMG_INIT_EAGER=1 keeps the one-sweep-per-round kernels (also the NCCL path).
-  // (measured at 8192^2: k = 16 takes 5.0 ms lazily against 3.7 ms with full sweeps, k = 64 11.6 against
-  // 15.7, k = 256 36 against 63 — the lazy launch pays off once there are many rounds)
+  // (measured at 8192^2: k = 16 takes 5.0 ms lazily against 3.7 ms with full sweeps, k = 64 9.7 against
+  // 15.7, k = 256 27.5 against 63 — the lazy launch pays off once there are many rounds)
   if ((!dist || fused) && j->k > std::max<uint32_t>(ctx->init_lazy_min_k, (uint32_t)ctx->init_eager_rounds + 1) && !ctx->init_eager) {
     unsigned short* ub = (unsigned short*)((unsigned char*)j->dmin + dmin_part(n * 4));
     unsigned short* fold = (unsigned short*)((unsigned char*)ub + dmin_part(n * 2));
